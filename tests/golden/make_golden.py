@@ -1,0 +1,155 @@
+"""Generates the committed golden fixtures in tests/golden/ FROM THE REFERENCE ITSELF.
+
+Run in the build container only (needs /root/reference):  python tests/golden/make_golden.py
+
+* segment_cases.npz / segment_expect.json -- the five bundled reference cases cropped to the
+  ROI bbox (raw intensities + mask), the reference's own golden matrices
+  data/baseline/<case>_<class>.npy (what reference tests/test_matrices.py:35-65 checks) and
+  the feature columns of data/baseline/baseline_<class>.csv that depend only on hot-path
+  settings (what reference tests/test_features.py checks).
+* voxel_*.npz -- feature maps produced by the (patched, see oracle/ref_harness.py) reference
+  feature classes in voxel-based mode on small seeded volumes; no reference test pins voxel
+  mode, so these runs of the reference are the pin.
+* voxmat_*.npz -- dense per-voxel matrices from the reference `_cmatrices` (voxel mode).
+"""
+from __future__ import annotations
+
+import ast
+import csv
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
+import ref_harness as rh  # noqa: E402
+
+rad = rh.load_reference()
+import SimpleITK as sitk  # noqa: E402  (stub)
+from radiomics import glcm, gldm, glrlm, glszm, ngtdm  # noqa: E402
+
+CLASSES = {
+    "glcm": glcm.RadiomicsGLCM, "glrlm": glrlm.RadiomicsGLRLM, "glszm": glszm.RadiomicsGLSZM,
+    "gldm": gldm.RadiomicsGLDM, "ngtdm": ngtdm.RadiomicsNGTDM,
+}
+CASES = ["brain1", "brain2", "breast1", "lung1", "lung2"]
+HOT_KEYS = {"binWidth", "binCount", "label", "distances", "force2D", "force2Ddimension",
+            "symmetricalGLCM", "weightingNorm", "gldm_a"}
+# settings that alter the image/mask before the hot path (need SimpleITK) -> column skipped
+PRE_KEYS = {"normalize", "resampledPixelSpacing", "resegmentRange", "preCrop", "correctMask"}
+
+
+def segment_goldens():
+    arrays, expect = {}, {}
+    for case in CASES:
+        img, m, sp = rh.load_case(case)
+        arrays[f"{case}_image"] = img
+        arrays[f"{case}_mask"] = m
+        arrays[f"{case}_spacing"] = np.array(sp)
+        for cname in CLASSES:
+            arrays[f"{case}_{cname}_P"] = np.load(
+                os.path.join(rh.REF_ROOT, "data", "baseline", f"{case}_{cname}.npy"))
+    for cname, cls in CLASSES.items():
+        rows = list(csv.reader(open(os.path.join(rh.REF_ROOT, "data", "baseline", f"baseline_{cname}.csv"))))
+        header = rows[0]
+        byname = {r[0]: r for r in rows}
+        for col in range(1, len(header)):
+            test = header[col]
+            case = byname["diagnostics_Configuration_TestCase"][col]
+            settings = ast.literal_eval(byname["diagnostics_Configuration_Settings"][col])
+            if any(settings.get(k) not in (None, False, [], 0) for k in PRE_KEYS):
+                continue
+            kw = {k: v for k, v in settings.items() if k in HOT_KEYS and v is not None}
+            feats = {}
+            for r in rows:
+                if r[0].startswith(f"original_{cname}_"):
+                    feats[r[0].split("_", 2)[2]] = float(r[col])
+            # cross-check: the reference run here must reproduce its own baseline
+            img, m, sp = rh.load_case(case)
+            obj = cls(sitk.Image(img, sp), sitk.Image(m.astype(np.uint8), sp), **kw)
+            got = obj.execute()
+            worst = max(abs(float(got[f]) - v) / max(abs(v), 1e-300) for f, v in feats.items())
+            assert worst < 1e-9, (cname, test, worst)
+            expect.setdefault(cname, {})[test] = {"case": case, "settings": kw, "features": feats}
+            print("segment", cname, test, "ok rel", worst)
+    np.savez_compressed(os.path.join(HERE, "segment_cases.npz"), **arrays)
+    json.dump(expect, open(os.path.join(HERE, "segment_expect.json"), "w"), indent=0, sort_keys=True)
+
+
+def voxel_volumes():
+    vols = {}
+    rng = np.random.default_rng(0)
+    # (a) BASELINE.json config-2 generator at toy size: iid uniform levels 1..32, full mask
+    vols["uniform32"] = dict(image=rng.integers(1, 33, (7, 8, 9)).astype(np.int32),
+                             mask=np.ones((7, 8, 9), bool), kw=dict(binWidth=1))
+    # (b) smooth field, few levels per window, ragged mask (holes + border cut)
+    z, y, x = np.meshgrid(np.arange(8), np.arange(9), np.arange(10), indexing="ij")
+    sm = 40 * np.sin(z / 3.0) + 30 * np.cos(y / 4.0) + 25 * np.sin(x / 2.5) + rng.normal(0, 4, z.shape)
+    msk = ((z - 3.5) ** 2 / 16 + (y - 4) ** 2 / 20 + (x - 4.5) ** 2 / 26) <= 1.0
+    msk &= rng.random(z.shape) > 0.07
+    vols["smooth_ragged"] = dict(image=np.round(sm * 4).astype(np.int32), mask=msk, kw=dict(binWidth=25))
+    # (c) 8 levels, kernelRadius 2, distances [1,2]
+    vols["r2_d12"] = dict(image=rng.integers(1, 9, (6, 7, 6)).astype(np.int32),
+                          mask=rng.random((6, 7, 6)) > 0.1,
+                          kw=dict(binWidth=1, kernelRadius=2, distances=[1, 2]))
+    # (d) force2D + asymmetric GLCM + gldm_a=1
+    vols["force2d_asym"] = dict(image=rng.integers(1, 6, (4, 8, 8)).astype(np.int32),
+                                mask=rng.random((4, 8, 8)) > 0.05,
+                                kw=dict(binWidth=1, force2D=True, force2Ddimension=0,
+                                        symmetricalGLCM=False, gldm_a=1))
+    # (e) weighted GLCM/GLRLM (anisotropic spacing)
+    vols["weighted"] = dict(image=rng.integers(1, 7, (5, 6, 7)).astype(np.int32),
+                            mask=np.ones((5, 6, 7), bool), spacing=(0.8, 0.8, 2.5),
+                            kw=dict(binWidth=1, weightingNorm="euclidean"))
+    return vols
+
+
+def voxel_goldens():
+    for name, v in voxel_volumes().items():
+        sp = v.get("spacing", (1.0, 1.0, 1.0))
+        out = {"image": v["image"], "mask": v["mask"], "spacing": np.array(sp),
+               "settings": np.array(json.dumps(v["kw"]))}
+        for cname, cls in CLASSES.items():
+            obj = cls(sitk.Image(v["image"], sp), sitk.Image(v["mask"].astype(np.uint8), sp),
+                      voxelBased=True, **v["kw"])
+            res = obj.execute()
+            for f, im in res.items():
+                out[f"{cname}_{f}"] = sitk.GetArrayFromImage(im)
+            print("voxel", name, cname, len(res))
+            if cname == "glcm":
+                # Reference defect: one voxel with an empty angle makes
+                # eigvals raise and the WHOLE batch's MCC map stays at initValue.  Pin the
+                # per-voxel meaning with voxelBatch=1 (each voxel its own batch -> empty angles
+                # are dropped per voxel, failures stay local).
+                o1 = cls(sitk.Image(v["image"], sp), sitk.Image(v["mask"].astype(np.uint8), sp),
+                         voxelBased=True, voxelBatch=1, **v["kw"])
+                o1.enableFeatureByName("MCC")
+                import logging
+                logging.getLogger("radiomics").setLevel(logging.CRITICAL)
+                out["glcm_MCC_voxelBatch1"] = sitk.GetArrayFromImage(o1.execute()["MCC"])
+                logging.getLogger("radiomics").setLevel(logging.INFO)
+        np.savez_compressed(os.path.join(HERE, f"voxel_{name}.npz"), **out)
+
+
+def voxmat_goldens():
+    """dense per-voxel matrices straight from the reference C extension (integer parity)."""
+    cm = rad.cMatrices
+    rng = np.random.default_rng(1)
+    img = rng.integers(1, 7, (5, 6, 7)).astype(np.int32)
+    msk = rng.random((5, 6, 7)) > 0.15
+    vox = np.array(np.where(msk)).astype(np.int32)
+    out = {"image": img, "mask": msk, "voxels": vox}
+    out["glcm"], out["glcm_angles"] = cm.calculate_glcm(img, msk, np.array([1]), 6, False, 0, 1, vox)
+    out["glrlm"], out["glrlm_angles"] = cm.calculate_glrlm(img, msk, 6, 7, False, 0, 1, vox)
+    out["glszm"] = cm.calculate_glszm(img, msk, 6, int(msk.sum()), False, 0, 1, vox)
+    out["gldm"] = cm.calculate_gldm(img, msk, np.array([1]), 6, 0, False, 0, 1, vox)
+    out["ngtdm"] = cm.calculate_ngtdm(img, msk, np.array([1]), 6, False, 0, 1, vox)
+    np.savez_compressed(os.path.join(HERE, "voxmat_small.npz"), **out)
+
+
+if __name__ == "__main__":
+    segment_goldens()
+    voxmat_goldens()
+    voxel_goldens()
