@@ -1,0 +1,117 @@
+/* b200radiomics -- C ABI of the B200-native texture-matrix engine (libb200radiomics.so).
+ *
+ * Drop-in boundary for the hot path of AIM-Harvard/pyradiomics: the C
+ * functions of reference radiomics/src/cmatrices.h:1-8 and the per-voxel driver loops of
+ * reference radiomics/src/_cmatrices.c (set_bb + `for v < Nvox` at :203-207, :355-377, :550-569,
+ * :699-717, :848-867), plus fused entry points that go from the quantised volume straight to the
+ * per-voxel feature maps (what radiomics/{glcm,glrlm,glszm,gldm,ngtdm}.py compute from the dense
+ * matrices in voxel-based mode).  Plain pointers and sizes only; no torch / numpy types.
+ *
+ * Conventions
+ *   - volumes are C-contiguous (z,y,x); 2-D images are passed with nd == 2 (y,x).
+ *   - `*_host` entry points take HOST pointers and do their own transfers; `*_dev` entry points
+ *     take DEVICE pointers plus a `cudaStream_t` passed as `void *stream` (NULL = default stream)
+ *     and are asynchronous with respect to the host unless stated otherwise.
+ *   - every function returns RB_OK (0) or a negative rb_status; rb_last_error() gives the text.
+ *   - gray levels inside the mask must lie in 1..Ng; anything else gives RB_ERR_LEVEL_RANGE, the
+ *     analogue of the reference's IndexError("Calculation of <M> Failed.")
+ *     (radiomics/src/_cmatrices.c:219,372,566,714,864).
+ *   - there is no CPU fallback: without a usable CUDA device every compute entry point fails with
+ *     RB_ERR_CUDA.
+ */
+#ifndef B200RADIOMICS_H
+#define B200RADIOMICS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  RB_OK = 0,
+  RB_ERR_CUDA = -1,         /* CUDA runtime error / no device                       */
+  RB_ERR_LEVEL_RANGE = -2,  /* gray level <= 0 or > Ng inside the mask (IndexError)   */
+  RB_ERR_ARG = -3,          /* bad argument (reference: ValueError / RuntimeError)    */
+  RB_ERR_NOMEM = -4,        /* allocation failure (reference: MemoryError)            */
+  RB_ERR_UNSUPPORTED = -5   /* outside the implemented envelope        */
+} rb_status;
+
+typedef enum { RB_GLCM = 0, RB_GLRLM = 1, RB_GLSZM = 2, RB_GLDM = 3, RB_NGTDM = 4 } rb_class;
+
+/* weightingNorm of reference radiomics/glcm.py:105-108, glrlm.py:80-82 */
+typedef enum { RB_W_NONE = 0, RB_W_INFINITY = 1, RB_W_EUCLIDEAN = 2, RB_W_MANHATTAN = 3, RB_W_NO_WEIGHTING = 4 } rb_weighting;
+
+/* Hot-path settings (the kwargs of the reference feature classes). */
+typedef struct {
+  int kernelRadius;        /* voxel-based kernel radius, >= 1                         */
+  int force2D;             /* 0/1                                                     */
+  int force2Ddimension;    /* 0 = z, 1 = y, 2 = x                                     */
+  int ndist;               /* number of entries used in distances[] (GLCM/GLDM/NGTDM) */
+  int distances[8];
+  int symmetricalGLCM;     /* 0/1                                                     */
+  int weighting;           /* rb_weighting (GLCM, GLRLM)                              */
+  double spacing_zyx[3];   /* voxel spacing, only used for weighting                  */
+  int gldm_a;              /* GLDM alpha                                              */
+  double initValue;        /* value of non-computed voxels in the feature maps        */
+  int Ng;                  /* max gray level in the ROI (coefficients["Ng"])          */
+  int n_roi_levels;        /* number of distinct gray levels in the ROI               */
+} rb_voxel_settings;
+
+/* ---- bookkeeping -------------------------------------------------------------------------- */
+const char *rb_last_error(void);
+const char *rb_version(void);
+int rb_device_count(void);          /* >= 0, or RB_ERR_CUDA                                   */
+int rb_num_features(int cls);       /* 24 / 16 / 16 / 14 / 5                                  */
+/* name of feature `idx` of class `cls` (the reference's get<Name>FeatureValue names, in the
+ * alphabetical order in which the reference enumerates them, radiomics/base.py:163-179). */
+const char *rb_feature_name(int cls, int idx);
+
+/* ---- neighbour offsets: replaces get_angle_count + build_angles (cmatrices.c:756-892) and
+ *      cmatrices_generate_angles (_cmatrices.c:882-924).  `angles` receives Na x nd ints; returns
+ *      Na (> 0), RB_ERR_ARG for an invalid distance / no angle, or the required count negated
+ *      minus 1000 if max_angles is too small. */
+int rb_generate_angles(const int *size, int nd, const int *distances, int ndist, int bidirectional,
+                       int force2D, int force2Ddimension, int *angles, int max_angles);
+
+/* ---- quantised volume on the device --------------------------------------------------------
+ * Fold image (int32 gray levels) and mask into the engine's compact level volume: level where
+ * mask != 0, 0 elsewhere; 1 byte per voxel when Ng <= 255, else 2.  Also validates 1..Ng and
+ * histograms the levels (presence[g-1] += 1, presence has Ng uint32 entries, may be NULL).
+ * status_dev (device int, zero-initialised by the caller, may be NULL) gets bit 0 set on a range
+ * violation.  Replaces the int32/bool coercion of try_parse_arrays (_cmatrices.c:1023-1085). */
+int rb_level_bytes(int Ng);  /* 1 or 2 */
+int rb_pack_levels_dev(const int32_t *image_dev, const uint8_t *mask_dev, long long nvoxels, int Ng,
+                       void *levels_dev, uint32_t *presence_dev, int *status_dev, void *stream);
+
+/* ---- fused voxel-based feature maps (the headline path) ------------------------------------
+ * For every voxel (z,y,x) with z0 <= z < z1 of a (Z,Y,X) level volume: if it is a centre voxel
+ * (centers_dev[i] != 0, or levels != 0 when centers_dev is NULL) compute all features of class
+ * `cls` over its (2r+1)^3 kernel window and store them; otherwise store settings->initValue.
+ * Feature f of voxel (z,y,x) goes to
+ *     out[f * out_feature_stride + ((z - out_z0) * Y + y) * X + x]
+ * as float64 (out_is_f32 == 0, the reference's map dtype, base.py:205-209) or float32.
+ * Angles that are empty for every voxel of the ROI are "deleted" like in the reference
+ * (glcm.py:187-196); rb_glcm_alive_angles_dev computes that set (32-bit words, bit a = angle a,
+ * RB_ALIVE_WORDS words, zero-initialised by the caller) and alive_dev may be NULL to keep all.
+ * status_dev: bit 0 = MCC eigen-problem larger than the in-kernel solver (value set to NaN),
+ *             bit 1 = weighted GLCM entry overflow. */
+#define RB_ALIVE_WORDS 6
+int rb_glcm_alive_angles_dev(const void *levels_dev, int level_bytes, const uint8_t *centers_dev,
+                             int Z, int Y, int X, const rb_voxel_settings *settings,
+                             uint32_t *alive_dev, void *stream);
+int rb_voxel_features_dev(int cls, const void *levels_dev, int level_bytes, const uint8_t *centers_dev,
+                          int Z, int Y, int X, int z0, int z1, const rb_voxel_settings *settings,
+                          const uint32_t *alive_host, void *out_dev, int out_is_f32,
+                          long long out_feature_stride, int out_z0, int *status_dev, void *stream);
+
+/* Host-buffer convenience (what a ctypes/cgo caller with NumPy-like arrays uses; e2e path):
+ * image int32 + mask bytes (nonzero = ROI; levels must already be discretised, 1..Ng) in, float64
+ * maps out: maps[f][z][y][x], f < rb_num_features(cls).  Synchronous. */
+int rb_voxel_features_host(int cls, const int32_t *image, const uint8_t *mask, int Z, int Y, int X,
+                           const rb_voxel_settings *settings, double *maps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RADIOMICS_H */

@@ -1,0 +1,162 @@
+// extern "C" surface of libb200radiomics.so (declared in include/b200radiomics.h).
+#include <stdarg.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "host_common.hpp"
+
+namespace rb {
+
+std::string& last_error_ref() {
+  static thread_local std::string s;
+  return s;
+}
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+
+int voxel_features_generic(int cls, const void* lev, int level_bytes, const uint8_t* centers, const VoxParams& P,
+                           double* out, long long fstride, int z0, int z1, int out_z0, int* status, cudaStream_t st);
+int glcm_alive_angles(const void* lev, int level_bytes, const uint8_t* centers, const VoxParams& P, uint32_t* alive,
+                      cudaStream_t st);
+int pack_levels(const int32_t* image, const uint8_t* mask, long long n, int Ng, void* lev, uint32_t* presence,
+                int* status, cudaStream_t st);
+
+static const char* kGlcmNames[] = {"Autocorrelation", "ClusterProminence", "ClusterShade", "ClusterTendency", "Contrast",
+  "Correlation", "DifferenceAverage", "DifferenceEntropy", "DifferenceVariance", "Id", "Idm", "Idmn", "Idn", "Imc1", "Imc2",
+  "InverseVariance", "JointAverage", "JointEnergy", "JointEntropy", "MCC", "MaximumProbability", "SumAverage", "SumEntropy",
+  "SumSquares"};
+static const char* kGlrlmNames[] = {"GrayLevelNonUniformity", "GrayLevelNonUniformityNormalized", "GrayLevelVariance",
+  "HighGrayLevelRunEmphasis", "LongRunEmphasis", "LongRunHighGrayLevelEmphasis", "LongRunLowGrayLevelEmphasis",
+  "LowGrayLevelRunEmphasis", "RunEntropy", "RunLengthNonUniformity", "RunLengthNonUniformityNormalized", "RunPercentage",
+  "RunVariance", "ShortRunEmphasis", "ShortRunHighGrayLevelEmphasis", "ShortRunLowGrayLevelEmphasis"};
+static const char* kGlszmNames[] = {"GrayLevelNonUniformity", "GrayLevelNonUniformityNormalized", "GrayLevelVariance",
+  "HighGrayLevelZoneEmphasis", "LargeAreaEmphasis", "LargeAreaHighGrayLevelEmphasis", "LargeAreaLowGrayLevelEmphasis",
+  "LowGrayLevelZoneEmphasis", "SizeZoneNonUniformity", "SizeZoneNonUniformityNormalized", "SmallAreaEmphasis",
+  "SmallAreaHighGrayLevelEmphasis", "SmallAreaLowGrayLevelEmphasis", "ZoneEntropy", "ZonePercentage", "ZoneVariance"};
+static const char* kGldmNames[] = {"DependenceEntropy", "DependenceNonUniformity", "DependenceNonUniformityNormalized",
+  "DependenceVariance", "GrayLevelNonUniformity", "GrayLevelVariance", "HighGrayLevelEmphasis", "LargeDependenceEmphasis",
+  "LargeDependenceHighGrayLevelEmphasis", "LargeDependenceLowGrayLevelEmphasis", "LowGrayLevelEmphasis",
+  "SmallDependenceEmphasis", "SmallDependenceHighGrayLevelEmphasis", "SmallDependenceLowGrayLevelEmphasis"};
+static const char* kNgtdmNames[] = {"Busyness", "Coarseness", "Complexity", "Contrast", "Strength"};
+static const char** kNames[5] = {kGlcmNames, kGlrlmNames, kGlszmNames, kGldmNames, kNgtdmNames};
+
+static VoxSettings to_settings(const rb_voxel_settings* s) {
+  VoxSettings v;
+  static_assert(sizeof(VoxSettings) == sizeof(rb_voxel_settings), "settings mirror out of sync");
+  memcpy(&v, s, sizeof v);
+  return v;
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+extern "C" {
+
+const char* rb_last_error(void) { return last_error_ref().c_str(); }
+const char* rb_version(void) { return "b200radiomics 0.1 (sm_100a)"; }
+
+int rb_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return fail(RB_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  return n;
+}
+
+int rb_num_features(int cls) { return (cls < 0 || cls > 4) ? RB_ERR_ARG : kNumFeatures[cls]; }
+
+const char* rb_feature_name(int cls, int idx) {
+  if (cls < 0 || cls > 4 || idx < 0 || idx >= kNumFeatures[cls]) return NULL;
+  return kNames[cls][idx];
+}
+
+int rb_generate_angles(const int* size, int nd, const int* distances, int ndist, int bidirectional, int force2D,
+                       int force2Ddimension, int* angles, int max_angles) {
+  if (!size || !distances || nd < 1 || nd > 3 || ndist < 1) return fail(RB_ERR_ARG, "bad size/distances");
+  std::vector<int> out;
+  int na = generate_angles(size, nd, distances, ndist, bidirectional != 0, force2D ? force2Ddimension : -1, out);
+  if (na <= 0) return fail(RB_ERR_ARG, "Error getting angle count.");
+  if (na > max_angles) return -1000 - na;
+  memcpy(angles, out.data(), sizeof(int) * (size_t)na * nd);
+  return na;
+}
+
+int rb_level_bytes(int Ng) { return Ng <= 255 ? 1 : 2; }
+
+int rb_pack_levels_dev(const int32_t* image_dev, const uint8_t* mask_dev, long long nvoxels, int Ng, void* levels_dev,
+                       uint32_t* presence_dev, int* status_dev, void* stream) {
+  return pack_levels(image_dev, mask_dev, nvoxels, Ng, levels_dev, presence_dev, status_dev, (cudaStream_t)stream);
+}
+
+int rb_glcm_alive_angles_dev(const void* levels_dev, int level_bytes, const uint8_t* centers_dev, int Z, int Y, int X,
+                             const rb_voxel_settings* settings, uint32_t* alive_dev, void* stream) {
+  VoxParams P;
+  if (fill_vox_params(C_GLCM, Z, Y, X, to_settings(settings), P)) return fail(RB_ERR_ARG, "bad voxel settings");
+  return glcm_alive_angles(levels_dev, level_bytes, centers_dev, P, alive_dev, (cudaStream_t)stream);
+}
+
+int rb_voxel_features_dev(int cls, const void* levels_dev, int level_bytes, const uint8_t* centers_dev, int Z, int Y,
+                          int X, int z0, int z1, const rb_voxel_settings* settings, const uint32_t* alive_host,
+                          void* out_dev, int out_is_f32, long long out_feature_stride, int out_z0, int* status_dev,
+                          void* stream) {
+  if (cls < 0 || cls > 4) return fail(RB_ERR_ARG, "unknown texture class %d", cls);
+  if (out_is_f32) return fail(RB_ERR_UNSUPPORTED, "float32 maps not implemented yet");
+  if (z0 < 0 || z1 > Z || z0 > z1) return fail(RB_ERR_ARG, "bad z range");
+  VoxParams P;
+  if (fill_vox_params(cls, Z, Y, X, to_settings(settings), P)) return fail(RB_ERR_ARG, "bad voxel settings");
+  if (alive_host && cls == C_GLCM) memcpy(P.alive, alive_host, sizeof P.alive);
+  return voxel_features_generic(cls, levels_dev, level_bytes, centers_dev, P, (double*)out_dev, out_feature_stride, z0,
+                                z1, out_z0, status_dev, (cudaStream_t)stream);
+}
+
+int rb_voxel_features_host(int cls, const int32_t* image, const uint8_t* mask, int Z, int Y, int X,
+                           const rb_voxel_settings* settings, double* maps) {
+  if (cls < 0 || cls > 4) return fail(RB_ERR_ARG, "unknown texture class %d", cls);
+  const long long n = (long long)Z * Y * X;
+  const int nf = kNumFeatures[cls];
+  const int lb = rb_level_bytes(settings->Ng);
+  int32_t* d_img = NULL; uint8_t* d_msk = NULL; void* d_lev = NULL; double* d_out = NULL; int* d_status = NULL;
+  uint32_t* d_alive = NULL;
+  int rc = RB_OK;
+  auto cleanup = [&]() { cudaFree(d_img); cudaFree(d_msk); cudaFree(d_lev); cudaFree(d_out); cudaFree(d_status); cudaFree(d_alive); };
+#define RB_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { cleanup(); return fail(_e == cudaErrorMemoryAllocation ? RB_ERR_NOMEM : RB_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(_e)); } } while (0)
+  RB_TRY(cudaMalloc(&d_img, n * 4));
+  RB_TRY(cudaMalloc(&d_msk, n));
+  RB_TRY(cudaMalloc(&d_lev, n * lb));
+  RB_TRY(cudaMalloc(&d_out, sizeof(double) * n * nf));
+  RB_TRY(cudaMalloc(&d_status, 2 * sizeof(int)));
+  RB_TRY(cudaMalloc(&d_alive, RB_ALIVE_WORDS * 4));
+  RB_TRY(cudaMemsetAsync(d_status, 0, 2 * sizeof(int), 0));
+  RB_TRY(cudaMemsetAsync(d_alive, 0, RB_ALIVE_WORDS * 4, 0));
+  RB_TRY(cudaMemcpyAsync(d_img, image, n * 4, cudaMemcpyHostToDevice, 0));
+  RB_TRY(cudaMemcpyAsync(d_msk, mask, n, cudaMemcpyHostToDevice, 0));
+  rc = rb_pack_levels_dev(d_img, d_msk, n, settings->Ng, d_lev, NULL, d_status, 0);
+  uint32_t alive[RB_ALIVE_WORDS];
+  if (rc == RB_OK && cls == RB_GLCM) {
+    rc = rb_glcm_alive_angles_dev(d_lev, lb, NULL, Z, Y, X, settings, d_alive, 0);
+    if (rc == RB_OK) RB_TRY(cudaMemcpy(alive, d_alive, sizeof alive, cudaMemcpyDeviceToHost));
+  }
+  if (rc == RB_OK)
+    rc = rb_voxel_features_dev(cls, d_lev, lb, NULL, Z, Y, X, 0, Z, settings, cls == RB_GLCM ? alive : NULL, d_out, 0, n, 0,
+                               d_status + 1, 0);
+  if (rc == RB_OK) {
+    int st[2] = {0, 0};
+    RB_TRY(cudaMemcpy(st, d_status, sizeof st, cudaMemcpyDeviceToHost));
+    if (st[0] & 1) rc = fail(RB_ERR_LEVEL_RANGE, "gray level outside 1..Ng inside the mask");
+    else if (st[1] & 2) rc = fail(RB_ERR_UNSUPPORTED, "weighted GLCM entry list overflow");
+    else RB_TRY(cudaMemcpy(maps, d_out, sizeof(double) * n * nf, cudaMemcpyDeviceToHost));
+  }
+#undef RB_TRY
+  cleanup();
+  return rc;
+}
+
+}  // extern "C"

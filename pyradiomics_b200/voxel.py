@@ -1,0 +1,100 @@
+"""Voxel-based (feature-map) extraction on device-resident volumes: the headline path.
+
+Mirrors what the reference does per feature class in voxel-based mode (reference
+radiomics/base.py:98-111,200-245 + the per-class _calculateMatrix/_calculateCoefficients/get*
+methods) but as one fused CUDA kernel per class that never materialises per-voxel matrices.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CLASS_ID, CLASSES, check, lib
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def pack_levels(image: torch.Tensor, mask: torch.Tensor, Ng: int):
+    """int32 gray-level volume + mask (both CUDA) -> compact level volume (uint8 when Ng <= 255,
+    else int16 storage of uint16), 0 outside the mask; returns (levels, presence[Ng] int32 counts).
+    Raises IndexError when a masked voxel is outside 1..Ng (reference _cmatrices.c:219)."""
+    assert image.is_cuda and mask.is_cuda and image.shape == mask.shape
+    image = image.to(torch.int32).contiguous()
+    mask = (mask != 0).to(torch.uint8).contiguous()
+    lb = lib().rb_level_bytes(int(Ng))
+    lev = torch.empty(image.shape, dtype=torch.uint8 if lb == 1 else torch.int16, device=image.device)
+    presence = torch.zeros(int(Ng), dtype=torch.int32, device=image.device)
+    status = torch.zeros(1, dtype=torch.int32, device=image.device)
+    check(lib().rb_pack_levels_dev(_ptr(image), _ptr(mask), C.c_longlong(image.numel()), int(Ng), _ptr(lev),
+                                   _ptr(presence), _ptr(status), _stream()), "pack_levels")
+    if int(status.item()) & 1:
+        raise IndexError("gray level outside 1..Ng inside the mask")
+    return lev, presence
+
+
+def level_bytes(lev: torch.Tensor) -> int:
+    return 1 if lev.dtype == torch.uint8 else 2
+
+
+def glcm_alive_angles(lev, settings, centers=None):
+    Z, Y, X = lev.shape
+    alive = torch.zeros(_lib.ALIVE_WORDS, dtype=torch.int32, device=lev.device)
+    check(lib().rb_glcm_alive_angles_dev(_ptr(lev), level_bytes(lev), _ptr(centers), Z, Y, X, C.byref(settings),
+                                         _ptr(alive), _stream()), "glcm_alive_angles")
+    return alive.cpu().numpy().view(np.uint32).copy()
+
+
+def voxel_features(cls: str, lev: torch.Tensor, settings, *, centers=None, z0=0, z1=None, out=None, out_z0=None,
+                   alive=None, status=None):
+    """Launch the fused kernel of one class on planes [z0,z1) of `lev` (Z,Y,X).  Returns `out`:
+    float64 tensor [F, z1-z0, Y, X] (allocated when None).  Asynchronous on the current stream."""
+    cid = CLASS_ID[cls]
+    Z, Y, X = lev.shape
+    z1 = Z if z1 is None else z1
+    nf = lib().rb_num_features(cid)
+    if out is None:
+        out = torch.empty((nf, z1 - z0, Y, X), dtype=torch.float64, device=lev.device)
+        out_z0 = z0
+    assert out.dtype == torch.float64 and out.is_contiguous() and out.shape[0] == nf
+    if out_z0 is None:
+        out_z0 = z0
+    if cls == "glcm" and alive is None:
+        alive = glcm_alive_angles(lev, settings, centers)
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=lev.device)
+    alive_p = alive.ctypes.data_as(C.c_void_p) if alive is not None else None
+    check(lib().rb_voxel_features_dev(cid, _ptr(lev), level_bytes(lev), _ptr(centers), Z, Y, X, int(z0), int(z1),
+                                      C.byref(settings), alive_p, _ptr(out), 0, C.c_longlong(out.stride(0)),
+                                      int(out_z0), _ptr(status), _stream()), cls)
+    return out
+
+
+def extract_maps(image, mask, classes=CLASSES, **kw):
+    """Convenience: discretised int volume + mask (numpy or CUDA tensors) -> {class: {feature: map}}
+    with maps as float64 CUDA tensors (Z,Y,X).  `image` must already hold gray levels 1..Ng inside
+    the mask (see imageoperations.bin_image for the discretisation kernel)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    img = torch.as_tensor(np.ascontiguousarray(image) if isinstance(image, np.ndarray) else image).to(dev)
+    msk = torch.as_tensor(np.ascontiguousarray(mask) if isinstance(mask, np.ndarray) else mask).to(dev)
+    if img.ndim == 2:
+        img, msk = img[None], msk[None]
+        if kw.get("force2D"):
+            kw = dict(kw, force2Ddimension=kw.get("force2Ddimension", 0) + 1)
+    Ng = int(torch.where(msk != 0, img, torch.zeros_like(img)).max().item())
+    lev, presence = pack_levels(img, msk, Ng)
+    n_levels = int((presence > 0).sum().item())
+    settings = _lib.make_settings(Ng, n_levels, **kw)
+    res = {}
+    for cls in classes:
+        out = voxel_features(cls, lev, settings)
+        res[cls] = {name: out[i] for i, name in enumerate(_lib.feature_names(cls))}
+    return res

@@ -1,0 +1,45 @@
+// TEST-ONLY: compiles the __host__ __device__ per-voxel feature math of
+// pyradiomics_b200/csrc/vox_features.cuh with g++ so the arithmetic can be checked against the
+// oracle on machines without a GPU.  Not part of the product (which has no CPU path).
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "../../pyradiomics_b200/csrc/host_common.hpp"
+
+using namespace rb;
+
+template <int WCAP>
+static void run(int cls, const uint16_t* lev, const uint8_t* centers, const VoxParams& P, double* out, int* status) {
+  const int nf = kNumFeatures[cls];
+  const long long nvox = (long long)P.Z * P.Y * P.X;
+  for (int z = 0; z < P.Z; z++) for (int y = 0; y < P.Y; y++) for (int x = 0; x < P.X; x++) {
+    long long i = ((long long)z * P.Y + y) * P.X + x;
+    bool c = centers ? centers[i] != 0 : lev[i] != 0;
+    if (!c) { for (int k = 0; k < nf; k++) out[k * nvox + i] = P.init_value; continue; }
+    uint16_t w[WCAP]; double f[32];
+    load_window<uint16_t>(lev, P, z, y, x, w);
+    switch (cls) {
+      case C_GLCM: if (P.weighted) glcm_voxel<WCAP, true>(w, P, f, status); else glcm_voxel<WCAP, false>(w, P, f, status); break;
+      case C_GLRLM: if (P.weighted) glrlm_voxel<WCAP, true>(w, P, f); else glrlm_voxel<WCAP, false>(w, P, f); break;
+      case C_GLSZM: glszm_voxel<WCAP>(w, P, f); break;
+      case C_GLDM: gldm_voxel<WCAP>(w, P, f); break;
+      case C_NGTDM: ngtdm_voxel<WCAP>(w, P, f); break;
+    }
+    for (int k = 0; k < nf; k++) out[k * nvox + i] = f[k];
+  }
+}
+
+extern "C" int emul_voxel_features(int cls, const uint16_t* lev, const uint8_t* centers, int Z, int Y, int X,
+                                   const VoxSettings* s, const uint32_t* alive, double* out) {
+  VoxParams P;
+  int rc = fill_vox_params(cls, Z, Y, X, *s, P);
+  if (rc) return rc;
+  if (alive) for (int k = 0; k < (NW_MAX + 31) / 32; k++) P.alive[k] = alive[k];
+  int status = 0;
+  int cap = window_capacity(P);
+  if (cap <= 27) run<27>(cls, lev, centers, P, out, &status);
+  else if (cap <= 125) run<125>(cls, lev, centers, P, out, &status);
+  else if (cap <= 343) run<343>(cls, lev, centers, P, out, &status);
+  else return -5;
+  return status;
+}

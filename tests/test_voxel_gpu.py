@@ -1,0 +1,95 @@
+"""GPU parity tests of the fused voxel-based feature kernels (through the C ABI)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import pipeline as PL
+from helpers import RTOL, assert_maps_close, binned, ref_map, voxel_goldens
+from pyradiomics_b200 import _lib, voxel
+
+pytestmark = pytest.mark.gpu
+
+
+def _maps_host(cname, lev, Ng, nlev, spacing=(1, 1, 1), **kw):
+    """all maps of one class through the HOST-buffer C-ABI entry point"""
+    L = _lib.lib()
+    img = np.ascontiguousarray(lev, dtype=np.int32)
+    msk = np.ascontiguousarray(lev != 0, dtype=np.uint8)
+    s = _lib.make_settings(Ng, nlev, spacing_zyx=spacing, **kw)
+    nf = L.rb_num_features(_lib.CLASS_ID[cname])
+    out = np.empty((nf,) + img.shape)
+    _lib.check(L.rb_voxel_features_host(_lib.CLASS_ID[cname], img.ctypes.data_as(C.c_void_p), msk.ctypes.data_as(C.c_void_p),
+                                        *img.shape, C.byref(s), out.ctypes.data_as(C.c_void_p)), cname)
+    return dict(zip(_lib.feature_names(cname), out))
+
+
+@pytest.mark.parametrize("name,z,kw", voxel_goldens(), ids=[g[0] for g in voxel_goldens()])
+def test_golden_maps_from_the_reference(name, z, kw):
+    lev, levels, Ng = binned(z, kw)
+    lev = np.where(z["mask"], lev, 0)
+    kw2 = {k: v for k, v in kw.items() if k not in ("binWidth", "binCount")}
+    for cname in _lib.CLASSES:
+        got = _maps_host(cname, lev, Ng, len(levels), spacing=z["spacing"][::-1], **kw2)
+        for f, arr in got.items():
+            assert_maps_close(arr, ref_map(z, cname, f), f"{name}/{cname}/{f}")
+
+
+def _random_volume(kind, shape, seed):
+    rng = np.random.default_rng(seed)
+    if kind == "uniform":
+        return rng.integers(1, 33, shape).astype(np.int32)
+    zz, yy, xx = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
+    f = np.sin(zz / 2.7) + np.cos(yy / 3.1) + np.sin(xx / 2.3 + 1) + 0.25 * rng.normal(size=shape)
+    q = np.quantile(f, np.linspace(0, 1, 33)[1:-1])
+    return (np.digitize(f, q) + 1).astype(np.int32)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "smooth"])
+def test_against_oracle_on_seeded_volume(kind):
+    """BASELINE.json config-2/3 generators at a size the oracle finishes in seconds"""
+    shape = (10, 11, 12)
+    lev = _random_volume(kind, shape, 0)
+    msk = np.ones(shape, bool)
+    levels = np.unique(lev)
+    for cname in _lib.CLASSES:
+        got = _maps_host(cname, lev, int(levels.max()), len(levels))
+        ref = PL.extract(cname, lev, msk, voxelBased=True, binWidth=1)
+        for f, arr in ref.items():
+            assert_maps_close(got[f][msk], arr, f"{kind}/{cname}/{f}")
+
+
+def test_level_range_error_is_loud():
+    lev = np.ones((4, 4, 4), np.int32)
+    lev[1, 1, 1] = 9
+    with pytest.raises(IndexError):
+        _maps_host("gldm", lev, 3, 2)
+
+
+@pytest.mark.parametrize("cname", _lib.CLASSES)
+def test_slab_and_reflection_properties_at_scale(cname):
+    """size-independent properties on a 96^3 volume: (i) computing z-slabs separately equals the
+    whole-volume maps bit for bit (the multi-GPU decomposition), (ii) reflecting the volume along
+    x reflects every map (texture matrices are reflection-invariant)."""
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    N = 96 if cname != "glcm" else 64
+    lev = torch.randint(1, 33, (N, N, N), device=dev, dtype=torch.uint8)
+    s = _lib.make_settings(32, 32)
+    whole = voxel.voxel_features(cname, lev, s)
+    parts = [voxel.voxel_features(cname, lev, s, z0=a, z1=b) for a, b in ((0, N // 3), (N // 3, N - 5), (N - 5, N))]
+    assert torch.equal(torch.cat(parts, 1), whole)
+    flipped = voxel.voxel_features(cname, lev.flip(2).contiguous(), s).flip(3)
+    a, b = whole.cpu().numpy(), flipped.cpu().numpy()
+    assert np.isfinite(a).all()
+    assert np.allclose(a, b, rtol=1e-9, atol=1e-12)
+
+
+def test_tensor_api_matches_host_api():
+    lev = _random_volume("smooth", (9, 9, 9), 5)
+    res = voxel.extract_maps(lev, np.ones_like(lev, bool), classes=("ngtdm", "gldm"))
+    for cname in ("ngtdm", "gldm"):
+        host = _maps_host(cname, lev, int(lev.max()), len(np.unique(lev)))
+        for f, t in res[cname].items():
+            assert np.array_equal(t.cpu().numpy(), host[f])
