@@ -1,5 +1,6 @@
 // extern "C" surface of libb200radiomics.so (declared in include/b200radiomics.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -28,6 +29,16 @@ int glcm_alive_angles(const void* lev, int level_bytes, const uint8_t* centers, 
                       cudaStream_t st);
 int pack_levels(const int32_t* image, const uint8_t* mask, long long n, int Ng, void* lev, uint32_t* presence,
                 int* status, cudaStream_t st);
+bool glcm_fast_applicable(int cls, int level_bytes, const VoxParams& P);
+int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P, double* out, long long fstride,
+                     int z0, int z1, int out_z0, cudaStream_t st);
+
+// B200_RADIOMICS_FORCE_GENERIC=1 routes everything through the generic kernels (used by the
+// tests to cross-check the fast paths on the GPU)
+static bool force_generic() {
+  const char* e = getenv("B200_RADIOMICS_FORCE_GENERIC");
+  return e && e[0] == '1';
+}
 
 static const char* kGlcmNames[] = {"Autocorrelation", "ClusterProminence", "ClusterShade", "ClusterTendency", "Contrast",
   "Correlation", "DifferenceAverage", "DifferenceEntropy", "DifferenceVariance", "Id", "Idm", "Idmn", "Idn", "Imc1", "Imc2",
@@ -113,6 +124,9 @@ int rb_voxel_features_dev(int cls, const void* levels_dev, int level_bytes, cons
   VoxParams P;
   if (fill_vox_params(cls, Z, Y, X, to_settings(settings), P)) return fail(RB_ERR_ARG, "bad voxel settings");
   if (alive_host && cls == C_GLCM) memcpy(P.alive, alive_host, sizeof P.alive);
+  if (!force_generic() && glcm_fast_applicable(cls, level_bytes, P))
+    return glcm_fast_launch(levels_dev, centers_dev, P, (double*)out_dev, out_feature_stride, z0, z1, out_z0,
+                            (cudaStream_t)stream);
   return voxel_features_generic(cls, levels_dev, level_bytes, centers_dev, P, (double*)out_dev, out_feature_stride, z0,
                                 z1, out_z0, status_dev, (cudaStream_t)stream);
 }

@@ -1,0 +1,287 @@
+// GLCM fast path: kernelRadius 1, full 3-D, distances [1] (13 angles), symmetrical, unweighted,
+// 8-bit levels.  Same semantics as glcm_voxel<> in vox_features.cuh (which stays the generic
+// fallback and the in-repo cross-check), restructured for the GPU:
+//   * the 27 window levels are compared once (351 compares) into per-position equality bitmasks;
+//   * co-occurrence multiplicities come from pairwise compares of (|a-b|, a+b) keys instead of a
+//     merged entry list; all "linear in p" features are exact integer sums;
+//   * every log2 is a table lookup (arguments are ratios of small integers);
+//   * MCC: the level graph's connectivity is decided with bitmask propagation; only a connected
+//     graph needs an eigen-solve (Jacobi on the symmetric n x n matrix P/sqrt(px px), n <= 19).
+// __host__ __device__ so tests/host_emul can check the arithmetic on the CPU (test-only).
+#pragma once
+#include "vox_features.cuh"
+
+#ifdef __CUDA_ARCH__
+#define RB_CTZ(x) (__ffs((int)(x)) - 1)
+#define RB_POPC(x) __popc((unsigned)(x))
+#else
+#define RB_CTZ(x) __builtin_ctz((unsigned)(x))
+#define RB_POPC(x) __builtin_popcount((unsigned)(x))
+#endif
+
+namespace rb {
+
+constexpr int GF_NA = 13;
+constexpr int GF_LOGT = 40;       // log2 table covers 0..2*18+1
+constexpr int GF_KT = 256;        // |a-b| tables
+
+struct GlcmFastTables {
+  // per angle (in processing order: 3 axis, 6 face-diagonal, 4 body-diagonal)
+  uint8_t orig[GF_NA];            // index of the angle in the reference order (alive bit)
+  uint8_t np[GF_NA];              // pairs per angle: 18 / 12 / 8
+  uint8_t pA[GF_NA][18], pB[GF_NA][18];      // window positions (z*9+y*3+x) of the two pair ends
+  double log2t[GF_LOGT];          // log2(c), log2t[0] = 0 (never used with weight)
+  double idm[GF_KT], idmn[GF_KT], id[GF_KT], idn[GF_KT], inv[GF_KT];   // by k = |i-j|
+};
+
+// Host-side construction (Ng = max gray level of the ROI, as used by Idmn / Idn).
+inline void glcm_fast_build_tables(GlcmFastTables& T, int Ng) {
+  // reference order of the 13 unidirectional distance-1 angles (cmatrices.c:843-860)
+  int ang[13][3], k = 0;
+  for (int z = 1; z >= -1; z--) for (int y = 1; y >= -1; y--) for (int x = 1; x >= -1; x--) {
+    if (k < 13) { ang[k][0] = z; ang[k][1] = y; ang[k][2] = x; k++; }
+  }
+  int slot = 0;
+  for (int want = 1; want <= 3; want++)        // number of moving dimensions
+    for (int a = 0; a < 13; a++) {
+      int nm = (ang[a][0] != 0) + (ang[a][1] != 0) + (ang[a][2] != 0);
+      if (nm != want) continue;
+      T.orig[slot] = (uint8_t)a;
+      int n = 0;
+      for (int z = 0; z < 3; z++) for (int y = 0; y < 3; y++) for (int x = 0; x < 3; x++) {
+        int z2 = z + ang[a][0], y2 = y + ang[a][1], x2 = x + ang[a][2];
+        if (z2 < 0 || z2 > 2 || y2 < 0 || y2 > 2 || x2 < 0 || x2 > 2) continue;
+        T.pA[slot][n] = (uint8_t)(z * 9 + y * 3 + x);
+        T.pB[slot][n] = (uint8_t)(z2 * 9 + y2 * 3 + x2);
+        n++;
+      }
+      T.np[slot] = (uint8_t)n;
+      for (int t = n; t < 18; t++) { T.pA[slot][t] = 0; T.pB[slot][t] = 0; }
+      slot++;
+    }
+  T.log2t[0] = 0;
+  for (int c = 1; c < GF_LOGT; c++) T.log2t[c] = log2((double)c);
+  for (int d = 0; d < GF_KT; d++) {
+    double kk = d;
+    T.idm[d] = 1.0 / (1.0 + kk * kk);
+    T.idmn[d] = 1.0 / (1.0 + kk * kk / ((double)Ng * Ng));
+    T.id[d] = 1.0 / (1.0 + kk);
+    T.idn[d] = 1.0 / (1.0 + kk / (double)Ng);
+    T.inv[d] = d ? 1.0 / (kk * kk) : 0.0;
+  }
+}
+
+// second largest |eigenvalue| of the symmetric matrix M(i,j) = n_ij / sqrt(R_i R_j) of one angle
+// whose level graph is connected.  w: 27 window levels, eq: equality masks (stride es).
+template <int NP>
+RB_HDN double glcm_fast_mcc_solve(const uint32_t* eq, int es, const uint8_t* pA, const uint8_t* pB,
+                                  uint32_t valid, uint32_t EA, uint32_t EB, uint32_t all) {
+  // level nodes = distinct levels among the endpoints: representative = lowest position bit
+  uint32_t reps = 0;
+  for (uint32_t m = all; m;) {
+    int v = RB_CTZ(m);
+    uint32_t e = eq[v * es];
+    reps |= 1u << RB_CTZ(e);
+    m &= ~e;
+  }
+  const int n = RB_POPC(reps);
+  if (n < 2) return 0.0;
+  double A[19 * 19];
+  double rs[19];
+  for (int i = 0; i < n * n; i++) A[i] = 0;
+  {
+    int i = 0;
+    for (uint32_t m = reps; m; m &= m - 1, i++) {
+      uint32_t e = eq[RB_CTZ(m) * es];
+      rs[i] = 1.0 / sqrt((double)(RB_POPC(e & EA) + RB_POPC(e & EB)));
+    }
+  }
+  for (int t = 0; t < NP; t++) {
+    if (!(valid >> t & 1u)) continue;
+    int ra = RB_CTZ(eq[pA[t] * es]), rb_ = RB_CTZ(eq[pB[t] * es]);
+    int i = RB_POPC(reps & ((1u << ra) - 1)), j = RB_POPC(reps & ((1u << rb_) - 1));
+    double m = rs[i] * rs[j];
+    A[i * n + j] += m;
+    A[j * n + i] += m;   // i == j: entry (i,i) counted twice, as the symmetrised matrix does
+  }
+  jacobi_eigenvalues(A, n, n);
+  double l1 = 0, l2 = 0;
+  for (int i = 0; i < n; i++) {
+    double v = fabs(A[i * n + i]);
+    if (v > l1) { l2 = l1; l1 = v; } else if (v > l2) l2 = v;
+  }
+  return l2;
+}
+
+struct GlcmAcc {
+  double sum[GLCM_NF];
+  int n_ok, n_imc2;
+  bool ja_nan;
+};
+
+// one angle (slot s) of one voxel.  tile: pointer to window position 0 with strides ty (y) / tz (z).
+template <int NP>
+RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es, uint32_t repmask,
+                           const GlcmFastTables& T, int s, const VoxParams& P, GlcmAcc& acc) {
+  const uint8_t* pA = T.pA[s];
+  const uint8_t* pB = T.pB[s];
+  int kd[NP], ks[NP];
+  uint32_t valid = 0, EA = 0, EB = 0;
+  int n = 0, Ssum = 0, Sab = 0, Sq = 0, Skd = 0;
+#pragma unroll
+  for (int t = 0; t < NP; t++) {
+    const int a = w[pA[t] * ws], b = w[pB[t] * ws];
+    const bool ok = a != 0 && b != 0;
+    kd[t] = ok ? (a > b ? a - b : b - a) : (0x1000 + t);   // sentinels never compare equal
+    ks[t] = ok ? a + b : (0x2000 + t);
+    if (ok) {
+      valid |= 1u << t; EA |= 1u << pA[t]; EB |= 1u << pB[t];
+      n++; Ssum += a + b; Sab += a * b; Sq += a * a + b * b; Skd += kd[t];
+    }
+  }
+  const int orig = T.orig[s];
+  if (n == 0) {
+    if (P.alive[orig >> 5] >> (orig & 31) & 1u) acc.ja_nan = true;
+    return;
+  }
+  // multiplicities: md = #pairs with the same |a-b|, ms = same a+b, nn = same unordered pair
+  int md[NP], ms[NP], nn[NP];
+#pragma unroll
+  for (int t = 0; t < NP; t++) { md[t] = 1; ms[t] = 1; nn[t] = 1; }
+#pragma unroll
+  for (int t = 0; t < NP; t++)
+#pragma unroll
+    for (int u = t + 1; u < NP; u++) {
+      const int ed = kd[t] == kd[u], es_ = ks[t] == ks[u], eb = ed & es_;
+      md[t] += ed; md[u] += ed; ms[t] += es_; ms[u] += es_; nn[t] += eb; nn[u] += eb;
+    }
+  // S = 2n entries' worth of counts.  Every moment below is an exact integer numerator over a
+  // power of S (no cancellation between rounded quantities).
+  const int S2 = 2 * n;
+  const double S = (double)S2, invS = 1.0 / S, invS2 = invS * invS;
+  const double ux = Ssum * invS;
+  const double ac = 2.0 * Sab * invS;
+  const double contrast = 2.0 * (double)(Sq - 2 * Sab) * invS;
+  const int vnum = S2 * Sq - Ssum * Ssum;                       // S^2 * var_x  (>= 0, exact)
+  const double sxx = vnum * invS2;
+  const double sxy = (double)(2 * Sab * S2 - Ssum * Ssum) * invS2;
+  const double ct = (double)(2 * (Sq + 2 * Sab) * S2 - 4 * Ssum * Ssum) * invS2;
+  const double da = 2.0 * Skd * invS;
+  const double dvar = (double)(2 * (Sq - 2 * Sab) * S2 - 4 * Skd * Skd) * invS2;
+  double cs = 0, cp = 0, idm = 0, idmn = 0, id = 0, idn = 0, inv = 0, lgE = 0, lgD = 0, lgS = 0;
+  int E2 = 0, cmax = 0;
+#pragma unroll
+  for (int t = 0; t < NP; t++) {
+    if (!(valid >> t & 1u)) continue;
+    const double dn = (double)(ks[t] * n - Ssum), d2 = dn * dn;   // (i+j-ux-uy) * n, an integer
+    cs += d2 * dn; cp += d2 * d2;
+    const int k = kd[t];
+    idm += T.idm[k]; idmn += T.idmn[k]; id += T.id[k]; idn += T.idn[k]; inv += T.inv[k];
+    const int c = k ? nn[t] : 2 * nn[t];   // count of the merged matrix entry this pair feeds
+    E2 += k ? 2 * nn[t] : 4 * nn[t];       // sum_entries count^2, spread over the nn pairs of the entry
+    if (c > cmax) cmax = c;
+    lgE += T.log2t[c]; lgD += T.log2t[2 * md[t]]; lgS += T.log2t[2 * ms[t]];
+  }
+  const double invn = 1.0 / n, invn2 = invn * invn;
+  const double lS = T.log2t[2 * n];
+  const double hxy = -2.0 * invS * (lgE - n * lS);
+  const double dent = -2.0 * invS * (lgD - n * lS);
+  const double sent = -2.0 * invS * (lgS - n * lS);
+  // marginal entropy HX0 = -sum_levels (R/S) log2(R/S),  R = endpoint multiplicity of the level
+  double rl = 0; int nlev = 0;
+  const uint32_t used = EA | EB;
+  for (uint32_t m = repmask & 0x7FFFFFFu; m; m &= m - 1) {
+    const uint32_t e = eq[RB_CTZ(m) * es];
+    if (!(e & used)) continue;
+    const int R = RB_POPC(e & EA) + RB_POPC(e & EB);
+    rl += R * T.log2t[R]; nlev++;
+  }
+  const double hx0 = lS - rl * invS;
+  // HX = HY = hx0 and HXY1 = HXY2 = 2*hx0 (sum_ij p log2(px py) = sum_i px log2 px + sum_j py log2 py);
+  // the reference's "+eps" inside each log2 shifts these by < 1e-13 and is dropped consistently.
+  const double hx = hx0, hxy2 = 2.0 * hx0, hxy1 = hxy2;
+  double f[GLCM_NF];
+  f[G_Autocorrelation] = ac; f[G_JointAverage] = ux;
+  f[G_ClusterProminence] = cp * invn2 * invn2 * invn; f[G_ClusterShade] = cs * invn2 * invn2; f[G_ClusterTendency] = ct;
+  f[G_Contrast] = contrast;
+  f[G_Correlation] = (vnum == 0) ? 1.0 : sxy / (sxx + EPS);
+  f[G_DifferenceAverage] = da; f[G_DifferenceEntropy] = dent; f[G_DifferenceVariance] = dvar;
+  f[G_JointEnergy] = E2 * invS2; f[G_JointEntropy] = hxy;
+  f[G_Imc1] = (hx != 0) ? (hxy - hxy1) / hx : 0.0;
+  // exactly independent margins give HXY2 == HXY in the reference (value 0); here the two are
+  // built from different table sums, so "equal" means equal to rounding
+  const double dxy = hxy2 - hxy;
+  f[G_Imc2] = (fabs(dxy) < 1e-12) ? 0.0 : sqrt(1.0 - exp(-2.0 * dxy));
+  f[G_Idm] = 2.0 * idm * invS; f[G_Idmn] = 2.0 * idmn * invS; f[G_Id] = 2.0 * id * invS; f[G_Idn] = 2.0 * idn * invS;
+  f[G_InverseVariance] = 2.0 * inv * invS;
+  f[G_MaximumProbability] = cmax * invS; f[G_SumAverage] = 2.0 * ux; f[G_SumEntropy] = sent; f[G_SumSquares] = sxx;
+  // ---- MCC
+  double mcc;
+  if (P.n_roi_levels < 2) mcc = 1.0;
+  else if (nlev < 2) mcc = 0.0;
+  else {
+    // connectivity of the level graph by mask propagation over the edges
+    uint32_t comp = 0;
+    bool connected;
+    {
+      uint32_t em[NP];
+#pragma unroll
+      for (int t = 0; t < NP; t++) em[t] = (valid >> t & 1u) ? (eq[pA[t] * es] | eq[pB[t] * es]) : 0u;
+#pragma unroll
+      for (int t = 0; t < NP; t++) if (!comp) comp = em[t];
+      for (int sweep = 0; sweep < NP; sweep++) {
+        const uint32_t before = comp;
+#pragma unroll
+        for (int t = 0; t < NP; t++) if (em[t] & comp) comp |= em[t];
+        if (comp == before) break;
+      }
+      uint32_t all = 0;
+#pragma unroll
+      for (int t = 0; t < NP; t++) all |= em[t];
+      connected = comp == all;
+    }
+    mcc = connected ? glcm_fast_mcc_solve<NP>(eq, es, pA, pB, valid, EA, EB, used) : 1.0;
+  }
+  f[G_MCC] = mcc;
+#pragma unroll
+  for (int k = 0; k < GLCM_NF; k++) if (k != G_Imc2) acc.sum[k] += f[k];
+  acc.n_ok++;
+  if (f[G_Imc2] == f[G_Imc2]) { acc.sum[G_Imc2] += f[G_Imc2]; acc.n_imc2++; }
+}
+
+// all 24 GLCM features of one voxel.  w: the 27 window levels (0 = unmasked / outside);
+// eq: scratch for 27 equality masks with element stride es (shared memory on the device).
+RB_HD void glcm_fast_voxel(const uint8_t* w, int ws, uint32_t* eq, int es, const GlcmFastTables& T,
+                           const VoxParams& P, double* out) {
+  uint32_t e[27];
+  int wl[27];
+#pragma unroll
+  for (int p = 0; p < 27; p++) { wl[p] = w[p * ws]; e[p] = wl[p] ? (1u << p) : 0u; }
+#pragma unroll
+  for (int p = 0; p < 27; p++)
+#pragma unroll
+    for (int q = p + 1; q < 27; q++) {
+      const bool same = wl[p] == wl[q] && wl[p] != 0;
+      if (same) { e[p] |= 1u << q; e[q] |= 1u << p; }
+    }
+  uint32_t repmask = 0;
+#pragma unroll
+  for (int p = 0; p < 27; p++) {
+    eq[p * es] = e[p];
+    if (e[p] && (e[p] & ((1u << p) - 1)) == 0) repmask |= 1u << p;
+  }
+  GlcmAcc acc;
+#pragma unroll
+  for (int k = 0; k < GLCM_NF; k++) acc.sum[k] = 0;
+  acc.n_ok = 0; acc.n_imc2 = 0; acc.ja_nan = false;
+  for (int s = 0; s < 3; s++) glcm_fast_angle<18>(w, ws, eq, es, repmask, T, s, P, acc);
+  for (int s = 3; s < 9; s++) glcm_fast_angle<12>(w, ws, eq, es, repmask, T, s, P, acc);
+  for (int s = 9; s < 13; s++) glcm_fast_angle<8>(w, ws, eq, es, repmask, T, s, P, acc);
+  const double inv = acc.n_ok ? 1.0 / acc.n_ok : NAN;
+#pragma unroll
+  for (int k = 0; k < GLCM_NF; k++) out[k] = acc.n_ok ? acc.sum[k] * inv : NAN;
+  out[G_Imc2] = acc.n_imc2 ? acc.sum[G_Imc2] / acc.n_imc2 : NAN;
+  if (acc.ja_nan) out[G_JointAverage] = NAN;
+}
+
+}  // namespace rb

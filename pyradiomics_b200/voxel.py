@@ -98,3 +98,57 @@ def extract_maps(image, mask, classes=CLASSES, **kw):
         out = voxel_features(cls, lev, settings)
         res[cls] = {name: out[i] for i, name in enumerate(_lib.feature_names(cls))}
     return res
+
+
+class HostExtractor:
+    """End-to-end voxel-based extraction with HOST buffers (what a pyradiomics user holds):
+    int32 gray levels + mask in, float64 feature maps out, all transfers inside.  Device buffers
+    and pinned staging are allocated once and reused; the device->host copy of class k overlaps
+    the kernels of class k+1 on a second stream."""
+
+    def __init__(self, shape, classes=CLASSES, device=None):
+        self.shape = tuple(int(s) for s in shape)
+        self.classes = tuple(classes)
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.nf = {c: lib().rb_num_features(CLASS_ID[c]) for c in self.classes}
+        n = int(np.prod(self.shape))
+        self.d_img = torch.empty(self.shape, dtype=torch.int32, device=self.dev)
+        self.d_msk = torch.empty(self.shape, dtype=torch.uint8, device=self.dev)
+        maxf = max(self.nf.values())
+        self.d_out = [torch.empty((maxf,) + self.shape, dtype=torch.float64, device=self.dev) for _ in range(2)]
+        self.h_img = torch.empty(self.shape, dtype=torch.int32, pin_memory=True)
+        self.h_msk = torch.empty(self.shape, dtype=torch.uint8, pin_memory=True)
+        self.h_out = {c: torch.empty((self.nf[c],) + self.shape, dtype=torch.float64, pin_memory=True) for c in self.classes}
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.h2d_bytes = n * 5
+        self.d2h_bytes = sum(self.nf.values()) * n * 8
+        self.launches = 0
+
+    def run(self, image: np.ndarray, mask: np.ndarray, Ng: int, n_roi_levels: int, **kw):
+        """returns {class: pinned float64 tensor [F,Z,Y,X]} (valid until the next run())."""
+        self.h_img.numpy()[...] = image
+        self.h_msk.numpy()[...] = mask
+        cur = torch.cuda.current_stream()
+        self.d_img.copy_(self.h_img, non_blocking=True)
+        self.d_msk.copy_(self.h_msk, non_blocking=True)
+        lev, _ = pack_levels(self.d_img, self.d_msk, Ng)
+        settings = _lib.make_settings(Ng, n_roi_levels, **kw)
+        self.launches = 1
+        done = [None, None]
+        for i, c in enumerate(self.classes):
+            slot = i & 1
+            if done[slot] is not None:
+                cur.wait_event(done[slot])          # the D2H that last used this device buffer
+            out = self.d_out[slot][: self.nf[c]]
+            voxel_features(c, lev, settings, out=out, out_z0=0)
+            self.launches += 2 if c == "glcm" else 1
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(ev)
+                self.h_out[c].copy_(out, non_blocking=True)
+                done[slot] = torch.cuda.Event()
+                done[slot].record(self.copy_stream)
+        self.copy_stream.synchronize()
+        cur.synchronize()
+        return self.h_out

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 
 #include "../../pyradiomics_b200/csrc/host_common.hpp"
+#include "../../pyradiomics_b200/csrc/glcm_fast.cuh"
 
 using namespace rb;
 
@@ -42,4 +43,28 @@ extern "C" int emul_voxel_features(int cls, const uint16_t* lev, const uint8_t* 
   else if (cap <= 343) run<343>(cls, lev, centers, P, out, &status);
   else return -5;
   return status;
+}
+
+// GLCM fast path (r=1, 13 angles, symmetric, unweighted, 8-bit levels) on the host
+extern "C" int emul_glcm_fast(const uint16_t* lev, int Z, int Y, int X, const VoxSettings* s, const uint32_t* alive,
+                              double* out) {
+  VoxParams P;
+  int rc = fill_vox_params(C_GLCM, Z, Y, X, *s, P);
+  if (rc) return rc;
+  if (alive) for (int k = 0; k < (NW_MAX + 31) / 32; k++) P.alive[k] = alive[k];
+  if (P.na != 13 || P.rz != 1 || P.ry != 1 || P.rx != 1 || !P.symmetric || P.weighted || s->Ng > 255) return -5;
+  GlcmFastTables* T = new GlcmFastTables;
+  glcm_fast_build_tables(*T, s->Ng);
+  const long long nvox = (long long)Z * Y * X;
+  for (int z = 0; z < Z; z++) for (int y = 0; y < Y; y++) for (int x = 0; x < X; x++) {
+    long long i = ((long long)z * Y + y) * X + x;
+    if (!lev[i]) { for (int k = 0; k < GLCM_NF; k++) out[k * nvox + i] = P.init_value; continue; }
+    uint16_t w16[27]; uint8_t w[27]; uint32_t eq[27]; double f[GLCM_NF];
+    load_window<uint16_t>(lev, P, z, y, x, w16);
+    for (int k = 0; k < 27; k++) w[k] = (uint8_t)w16[k];
+    glcm_fast_voxel(w, 1, eq, 1, *T, P, f);
+    for (int k = 0; k < GLCM_NF; k++) out[k * nvox + i] = f[k];
+  }
+  delete T;
+  return 0;
 }

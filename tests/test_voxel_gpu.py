@@ -93,3 +93,21 @@ def test_tensor_api_matches_host_api():
         host = _maps_host(cname, lev, int(lev.max()), len(np.unique(lev)))
         for f, t in res[cname].items():
             assert np.array_equal(t.cpu().numpy(), host[f])
+
+
+@pytest.mark.parametrize("kind", ["uniform", "smooth"])
+def test_glcm_fast_path_equals_generic_kernel(kind, monkeypatch):
+    """the r=1 GLCM fast kernel against the generic kernel (same C ABI, env switch) on 40^3"""
+    lev = torch.as_tensor(_random_volume(kind, (40, 40, 40), 2).astype(np.uint8)).cuda()
+    if kind == "smooth":
+        lev[5:9, 3:30, 7] = 0  # holes in the mask
+    s = _lib.make_settings(32, 32)
+    fast = voxel.voxel_features("glcm", lev, s).cpu().numpy()
+    monkeypatch.setenv("B200_RADIOMICS_FORCE_GENERIC", "1")
+    gen = voxel.voxel_features("glcm", lev, s).cpu().numpy()
+    monkeypatch.delenv("B200_RADIOMICS_FORCE_GENERIC")
+    names = _lib.feature_names("glcm")
+    for k, f in enumerate(names):
+        # MCC / Imc2 of near-degenerate angles are rounding noise in every implementation
+        atol = 1e-6 if f in ("MCC", "Imc2", "Imc1") else 1e-9
+        assert np.allclose(fast[k], gen[k], rtol=1e-7, atol=atol, equal_nan=True), f
