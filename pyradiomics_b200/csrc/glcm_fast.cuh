@@ -6,10 +6,17 @@
 //     merged entry list; all "linear in p" features are exact integer sums;
 //   * every log2 is a table lookup (arguments are ratios of small integers);
 //   * MCC: the level graph's connectivity is decided with bitmask propagation; only a connected
-//     graph needs an eigen-solve (Jacobi on the symmetric n x n matrix P/sqrt(px px), n <= 19).
+//     graph needs an eigen-solve (Householder tridiagonalisation + Sturm bisection on the symmetric n x n matrix
+//     P/sqrt(px px), n <= 19).
 // __host__ __device__ so tests/host_emul can check the arithmetic on the CPU (test-only).
 #pragma once
 #include "vox_features.cuh"
+#include "straightline.inc"
+#ifndef __CUDACC__
+#include <algorithm>
+using std::max;
+using std::min;
+#endif
 
 #ifdef __CUDA_ARCH__
 #define RB_CTZ(x) (__ffs((int)(x)) - 1)
@@ -104,12 +111,8 @@ RB_HDN double glcm_fast_mcc_solve(const uint32_t* eq, int es, const uint8_t* pA,
     A[i * n + j] += m;
     A[j * n + i] += m;   // i == j: entry (i,i) counted twice, as the symmetrised matrix does
   }
-  jacobi_eigenvalues(A, n, n);
-  double l1 = 0, l2 = 0;
-  for (int i = 0; i < n; i++) {
-    double v = fabs(A[i * n + i]);
-    if (v > l1) { l2 = l1; l1 = v; } else if (v > l2) l2 = v;
-  }
+  double dd[19], ee[19];
+  const double l2 = sym_second_largest_abs(A, n, n, dd, ee);
   return l2;
 }
 
@@ -119,24 +122,27 @@ struct GlcmAcc {
   bool ja_nan;
 };
 
-// one angle (slot s) of one voxel.  tile: pointer to window position 0 with strides ty (y) / tz (z).
+// one angle (slot s) of one voxel.  w: the 27 window levels (stride ws), eq: equality masks.
 template <int NP>
 RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es, uint32_t repmask,
                            const GlcmFastTables& T, int s, const VoxParams& P, GlcmAcc& acc) {
   const uint8_t* pA = T.pA[s];
   const uint8_t* pB = T.pB[s];
-  int kd[NP], ks[NP];
+  // key1 = (a+b) << 8 | |a-b| identifies the unordered level pair; key2 = |a-b|.  Invalid pairs
+  // (an end outside the mask / volume) get distinct large keys and sort behind the n valid ones.
+  int key1[NP], key2[NP];
   uint32_t valid = 0, EA = 0, EB = 0;
   int n = 0, Ssum = 0, Sab = 0, Sq = 0, Skd = 0;
 #pragma unroll
   for (int t = 0; t < NP; t++) {
     const int a = w[pA[t] * ws], b = w[pB[t] * ws];
     const bool ok = a != 0 && b != 0;
-    kd[t] = ok ? (a > b ? a - b : b - a) : (0x1000 + t);   // sentinels never compare equal
-    ks[t] = ok ? a + b : (0x2000 + t);
+    const int kd = a > b ? a - b : b - a, ks = a + b;
+    key1[t] = ok ? (ks << 8 | kd) : (0x100000 + t);
+    key2[t] = ok ? kd : (0x1000 + t);
     if (ok) {
       valid |= 1u << t; EA |= 1u << pA[t]; EB |= 1u << pB[t];
-      n++; Ssum += a + b; Sab += a * b; Sq += a * a + b * b; Skd += kd[t];
+      n++; Ssum += ks; Sab += a * b; Sq += a * a + b * b; Skd += kd;
     }
   }
   const int orig = T.orig[s];
@@ -144,17 +150,9 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
     if (P.alive[orig >> 5] >> (orig & 31) & 1u) acc.ja_nan = true;
     return;
   }
-  // multiplicities: md = #pairs with the same |a-b|, ms = same a+b, nn = same unordered pair
-  int md[NP], ms[NP], nn[NP];
-#pragma unroll
-  for (int t = 0; t < NP; t++) { md[t] = 1; ms[t] = 1; nn[t] = 1; }
-#pragma unroll
-  for (int t = 0; t < NP; t++)
-#pragma unroll
-    for (int u = t + 1; u < NP; u++) {
-      const int ed = kd[t] == kd[u], es_ = ks[t] == ks[u], eb = ed & es_;
-      md[t] += ed; md[u] += ed; ms[t] += es_; ms[u] += es_; nn[t] += eb; nn[u] += eb;
-    }
+  if (NP == 18) { RB_SORTNET_18(key1); RB_SORTNET_18(key2); }
+  else if (NP == 12) { RB_SORTNET_12(key1); RB_SORTNET_12(key2); }
+  else { RB_SORTNET_8(key1); RB_SORTNET_8(key2); }
   // S = 2n entries' worth of counts.  Every moment below is an exact integer numerator over a
   // power of S (no cancellation between rounded quantities).
   const int S2 = 2 * n;
@@ -168,19 +166,31 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
   const double ct = (double)(2 * (Sq + 2 * Sab) * S2 - 4 * Ssum * Ssum) * invS2;
   const double da = 2.0 * Skd * invS;
   const double dvar = (double)(2 * (Sq - 2 * Sab) * S2 - 4 * Skd * Skd) * invS2;
+  // scan the sorted keys: runs of equal key1 = merged matrix entries (length nn), runs of equal
+  // a+b = p_{x+y} bins, runs of equal key2 = p_{x-y} bins
   double cs = 0, cp = 0, idm = 0, idmn = 0, id = 0, idn = 0, inv = 0, lgE = 0, lgD = 0, lgS = 0;
-  int E2 = 0, cmax = 0;
+  int E2 = 0, cmax = 0, runK = 0, runS = 0, runD = 0;
 #pragma unroll
-  for (int t = 0; t < NP; t++) {
-    if (!(valid >> t & 1u)) continue;
-    const double dn = (double)(ks[t] * n - Ssum), d2 = dn * dn;   // (i+j-ux-uy) * n, an integer
-    cs += d2 * dn; cp += d2 * d2;
-    const int k = kd[t];
-    idm += T.idm[k]; idmn += T.idmn[k]; id += T.id[k]; idn += T.idn[k]; inv += T.inv[k];
-    const int c = k ? nn[t] : 2 * nn[t];   // count of the merged matrix entry this pair feeds
-    E2 += k ? 2 * nn[t] : 4 * nn[t];       // sum_entries count^2, spread over the nn pairs of the entry
-    if (c > cmax) cmax = c;
-    lgE += T.log2t[c]; lgD += T.log2t[2 * md[t]]; lgS += T.log2t[2 * ms[t]];
+  for (int i = 0; i < NP; i++) {
+    if (i < n) {
+      const int k1 = key1[i], ks = k1 >> 8, kd = k1 & 255;
+      const double dn = (double)(ks * n - Ssum), d2 = dn * dn;   // (i+j-ux-uy) * n, an integer
+      cs += d2 * dn; cp += d2 * d2;
+      idm += T.idm[kd]; idmn += T.idmn[kd]; id += T.id[kd]; idn += T.idn[kd]; inv += T.inv[kd];
+      const int nx1 = (i + 1 < NP) ? key1[i + 1 < NP ? i + 1 : i] : -1;
+      const int nx2 = (i + 1 < NP) ? key2[i + 1 < NP ? i + 1 : i] : -1;
+      const bool last = (i + 1 == n);
+      runK++; runS++; runD++;
+      if (last || nx1 != k1) {                 // end of a merged-entry run
+        const int c = kd ? runK : 2 * runK;    // count of the matrix entry (both orders when i != j)
+        E2 += kd ? 2 * runK * runK : 4 * runK * runK;
+        if (c > cmax) cmax = c;
+        lgE += runK * T.log2t[c];
+        runK = 0;
+      }
+      if (last || (nx1 >> 8) != ks) { lgS += runS * T.log2t[2 * runS]; runS = 0; }
+      if (last || nx2 != key2[i]) { lgD += runD * T.log2t[2 * runD]; runD = 0; }
+    }
   }
   const double invn = 1.0 / n, invn2 = invn * invn;
   const double lS = T.log2t[2 * n];
@@ -190,13 +200,17 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
   // marginal entropy HX0 = -sum_levels (R/S) log2(R/S),  R = endpoint multiplicity of the level
   double rl = 0; int nlev = 0;
   const uint32_t used = EA | EB;
-  for (uint32_t m = repmask & 0x7FFFFFFu; m; m &= m - 1) {
-    const uint32_t e = eq[RB_CTZ(m) * es];
-    if (!(e & used)) continue;
-    const int R = RB_POPC(e & EA) + RB_POPC(e & EB);
-    rl += R * T.log2t[R]; nlev++;
+#pragma unroll
+  for (int v = 0; v < 27; v++) {
+    if (repmask >> v & 1u) {
+      const uint32_t e = eq[v * es];
+      if (e & used) {
+        const int R = RB_POPC(e & EA) + RB_POPC(e & EB);
+        rl += R * T.log2t[R]; nlev++;
+      }
+    }
   }
-  const double hx0 = lS - rl * invS;
+  const double hx0 = nlev > 1 ? lS - rl * invS : 0.0;   // one level: exactly 0 (avoids 0/rounding in Imc1)
   // HX = HY = hx0 and HXY1 = HXY2 = 2*hx0 (sum_ij p log2(px py) = sum_i px log2 px + sum_j py log2 py);
   // the reference's "+eps" inside each log2 shifts these by < 1e-13 and is dropped consistently.
   const double hx = hx0, hxy2 = 2.0 * hx0, hxy1 = hxy2;
@@ -221,26 +235,21 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
   else if (nlev < 2) mcc = 0.0;
   else {
     // connectivity of the level graph by mask propagation over the edges
-    uint32_t comp = 0;
-    bool connected;
-    {
-      uint32_t em[NP];
+    uint32_t em[NP];
+    uint32_t comp = 0, all = 0;
 #pragma unroll
-      for (int t = 0; t < NP; t++) em[t] = (valid >> t & 1u) ? (eq[pA[t] * es] | eq[pB[t] * es]) : 0u;
-#pragma unroll
-      for (int t = 0; t < NP; t++) if (!comp) comp = em[t];
-      for (int sweep = 0; sweep < NP; sweep++) {
-        const uint32_t before = comp;
-#pragma unroll
-        for (int t = 0; t < NP; t++) if (em[t] & comp) comp |= em[t];
-        if (comp == before) break;
-      }
-      uint32_t all = 0;
-#pragma unroll
-      for (int t = 0; t < NP; t++) all |= em[t];
-      connected = comp == all;
+    for (int t = 0; t < NP; t++) {
+      em[t] = (valid >> t & 1u) ? (eq[pA[t] * es] | eq[pB[t] * es]) : 0u;
+      all |= em[t];
+      if (!comp) comp = em[t];
     }
-    mcc = connected ? glcm_fast_mcc_solve<NP>(eq, es, pA, pB, valid, EA, EB, used) : 1.0;
+    for (int sweep = 0; sweep < NP; sweep++) {
+      const uint32_t before = comp;
+#pragma unroll
+      for (int t = 0; t < NP; t++) if (em[t] & comp) comp |= em[t];
+      if (comp == before) break;
+    }
+    mcc = (comp == all) ? glcm_fast_mcc_solve<NP>(eq, es, pA, pB, valid, EA, EB, used) : 1.0;
   }
   f[G_MCC] = mcc;
 #pragma unroll
@@ -256,14 +265,8 @@ RB_HD void glcm_fast_voxel(const uint8_t* w, int ws, uint32_t* eq, int es, const
   uint32_t e[27];
   int wl[27];
 #pragma unroll
-  for (int p = 0; p < 27; p++) { wl[p] = w[p * ws]; e[p] = wl[p] ? (1u << p) : 0u; }
-#pragma unroll
-  for (int p = 0; p < 27; p++)
-#pragma unroll
-    for (int q = p + 1; q < 27; q++) {
-      const bool same = wl[p] == wl[q] && wl[p] != 0;
-      if (same) { e[p] |= 1u << q; e[q] |= 1u << p; }
-    }
+  for (int p = 0; p < 27; p++) wl[p] = w[p * ws];
+  RB_EQMASKS_27(wl, e);
   uint32_t repmask = 0;
 #pragma unroll
   for (int p = 0; p < 27; p++) {

@@ -120,35 +120,102 @@ struct Entries {
 RB_HD double xlog2(double p) { return p * log2(p + EPS); }
 
 // --------------------------------------------------------------------------------------------
-// symmetric Jacobi eigenvalues (cyclic), A is n x n with leading dimension ld, destroyed.
-static RB_HDN void jacobi_eigenvalues(double* A, int n, int ld) {
-  for (int sweep = 0; sweep < 40; sweep++) {
-    double off = 0, diag = 0;
-    for (int i = 0; i < n; i++) {
-      diag += A[i * ld + i] * A[i * ld + i];
-      for (int j = i + 1; j < n; j++) off += A[i * ld + j] * A[i * ld + j];
-    }
-    if (off <= 1e-30 * diag || off == 0) break;
-    for (int p = 0; p < n - 1; p++)
-      for (int q = p + 1; q < n; q++) {
-        double apq = A[p * ld + q];
-        if (fabs(apq) < 1e-300) continue;
-        double app = A[p * ld + p], aqq = A[q * ld + q];
-        double theta = (aqq - app) / (2.0 * apq);
-        double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-        for (int k = 0; k < n; k++) {  // columns p,q
-          double akp = A[k * ld + p], akq = A[k * ld + q];
-          A[k * ld + p] = c * akp - s * akq;
-          A[k * ld + q] = s * akp + c * akq;
+// Small dense symmetric eigenvalue machinery for MCC: Householder reduction to tridiagonal form
+// followed by Sturm-sequence bisection for ONE eigenvalue by index (no eigenvectors, no sweeps
+// to convergence: fixed trip counts, so a warp's lanes stay in step).
+//
+// Reduce the symmetric n x n matrix A (row-major, leading dimension ld, lower triangle used,
+// destroyed) to tridiagonal: diagonal d[0..n-1], sub-diagonal e[1..n-1] (e[0] = 0).
+static RB_HDN void sym_tridiagonalize(double* A, int n, int ld, double* d, double* e) {
+  for (int i = n - 1; i >= 1; i--) {
+    const int l = i - 1;
+    double h = 0, scale = 0;
+    if (l > 0) {
+      for (int k = 0; k <= l; k++) scale += fabs(A[i * ld + k]);
+      if (scale == 0) {
+        e[i] = A[i * ld + l];
+      } else {
+        const double inv = 1.0 / scale;
+        for (int k = 0; k <= l; k++) { A[i * ld + k] *= inv; h += A[i * ld + k] * A[i * ld + k]; }
+        double f = A[i * ld + l];
+        double g = f >= 0 ? -sqrt(h) : sqrt(h);
+        e[i] = scale * g;
+        h -= f * g;
+        A[i * ld + l] = f - g;
+        f = 0;
+        for (int j = 0; j <= l; j++) {
+          g = 0;
+          for (int k = 0; k <= j; k++) g += A[j * ld + k] * A[i * ld + k];
+          for (int k = j + 1; k <= l; k++) g += A[k * ld + j] * A[i * ld + k];
+          e[j] = g / h;
+          f += e[j] * A[i * ld + j];
         }
-        for (int k = 0; k < n; k++) {  // rows p,q
-          double apk = A[p * ld + k], aqk = A[q * ld + k];
-          A[p * ld + k] = c * apk - s * aqk;
-          A[q * ld + k] = s * apk + c * aqk;
+        const double hh = f / (h + h);
+        for (int j = 0; j <= l; j++) {
+          f = A[i * ld + j];
+          e[j] = g = e[j] - hh * f;
+          for (int k = 0; k <= j; k++) A[j * ld + k] -= f * e[k] + g * A[i * ld + k];
         }
       }
+    } else {
+      e[i] = A[i * ld + l];
+    }
+    d[i] = h;
   }
+  e[0] = 0;
+  for (int i = 0; i < n; i++) d[i] = A[i * ld + i];
+}
+
+// k-th smallest eigenvalue (k = 0..n-1) of the symmetric tridiagonal (d, e) inside [lo, hi],
+// by bisection on the number of sign changes of the division-free Sturm sequence.
+static RB_HDN double tridiag_kth_eigenvalue(const double* d, const double* e, int n, int k, double lo, double hi,
+                                            int iters) {
+  for (int it = 0; it < iters; it++) {
+    const double x = 0.5 * (lo + hi);
+    // p0 = 1, p1 = d0 - x, p_i = (d_i - x) p_{i-1} - e_i^2 p_{i-2}; #eigenvalues < x = sign changes
+    double pm2 = 1.0, pm1 = d[0] - x;
+    int cnt = pm1 <= 0;                      // a zero counts as an eigenvalue <= x
+    for (int i = 1; i < n; i++) {
+      const double e2 = e[i] * e[i];
+      if (e2 == 0) {                         // decoupled block: restart the sequence
+        pm2 = 1.0; pm1 = d[i] - x;
+        cnt += pm1 <= 0;
+        continue;
+      }
+      double p = (d[i] - x) * pm1 - e2 * pm2;
+      const bool neg_prev = pm1 < 0 || (pm1 == 0 && pm2 > 0);
+      const bool neg_cur = p < 0 || (p == 0 && !neg_prev);
+      cnt += neg_cur != neg_prev;
+      // rescale to stay far from over/underflow (signs are all that matter)
+      const double m = fabs(p) > fabs(pm1) ? fabs(p) : fabs(pm1);
+      if (m > 1e100 || (m < 1e-100 && m > 0)) { const double sc = 1.0 / m; p *= sc; pm1 *= sc; }
+      pm2 = pm1; pm1 = p;
+    }
+    if (cnt > k) hi = x; else lo = x;
+  }
+  return 0.5 * (lo + hi);
+}
+
+// Second-largest eigenvalue of a symmetric positive semi-definite matrix with spectrum in [0, 1+]
+// (the generic MCC path: A = M M^T).  n >= 2.
+static RB_HDN double sym_psd_second_largest(double* A, int n, int ld, double* d, double* e) {
+  if (n == 2) {                        // closed form: the two roots of the characteristic quadratic
+    const double tr = A[0] + A[ld + 1], det = A[0] * A[ld + 1] - A[ld] * A[ld];
+    const double disc = sqrt(fmax(tr * tr - 4.0 * det, 0.0));
+    return 0.5 * (tr - disc);
+  }
+  sym_tridiagonalize(A, n, ld, d, e);
+  return tridiag_kth_eigenvalue(d, e, n, n - 2, -1e-6, 1.0 + 1e-6, 46);
+}
+
+// Second-largest |eigenvalue| of a symmetric matrix with spectrum in [-1, 1] (the fast MCC path,
+// A = normalised co-occurrence D^-1/2 P D^-1/2 whose top eigenvalue is 1).  n >= 2.
+static RB_HDN double sym_second_largest_abs(double* A, int n, int ld, double* d, double* e) {
+  if (n == 2) return fabs(A[0] + A[ld + 1] - 1.0);     // eigenvalues are 1 and trace - 1
+  sym_tridiagonalize(A, n, ld, d, e);
+  const double top2 = tridiag_kth_eigenvalue(d, e, n, n - 2, -1.0 - 1e-6, 1.0 + 1e-6, 46);
+  const double bot = tridiag_kth_eigenvalue(d, e, n, 0, -1.0 - 1e-6, 1.0 + 1e-6, 46);
+  return fmax(fabs(top2), fabs(bot));
 }
 
 // --------------------------------------------------------------------------------------------
@@ -267,9 +334,8 @@ RB_HDN bool glcm_angle_features(const Entries<ECAP, W>& E, int n, const int* val
       A[ridx[l1] * nr + ridx[l2]] += m1 * m2;
     }
   }
-  jacobi_eigenvalues(A, nr, nr);
-  double l1 = -1e300, l2 = -1e300;
-  for (int k = 0; k < nr; k++) { double v = A[k * nr + k]; if (v > l1) { l2 = l1; l1 = v; } else if (v > l2) l2 = v; }
+  double dd[NJCAP], ee[NJCAP];
+  const double l2 = sym_psd_second_largest(A, nr, nr, dd, ee);
   f[G_MCC] = sqrt(l2 > 0 ? l2 : 0.0);
   return true;
 }
