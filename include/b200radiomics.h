@@ -111,6 +111,41 @@ int rb_voxel_features_dev(int cls, const void *levels_dev, int level_bytes, cons
 int rb_voxel_features_host(int cls, const int32_t *image, const uint8_t *mask, int Z, int Y, int X,
                            const rb_voxel_settings *settings, double *maps);
 
+/* ---- texture matrices: drop-ins for reference radiomics/src/cmatrices.h:1-8 plus the binding's
+ *      per-voxel driver (_cmatrices.c: calculate_glcm :84-233, glszm :235-430, glrlm :432-581,
+ *      ngtdm :583-730, gldm :732-880).  HOST pointers; synchronous.
+ *      image: int32 gray levels, mask: bytes (nonzero = ROI), size[nd] with nd = 2 or 3.
+ *      voxels == NULL  -> segment-based: one matrix over the whole array (nvox ignored).
+ *      voxels != NULL  -> int32 [nd][nvox] centre coordinates + kernelRadius > 0: one dense matrix
+ *                         per listed voxel over its clipped (2r+1)^nd box (force2D collapses one
+ *                         dimension), exactly the layout the reference returns:
+ *        glcm  [nvox][Ng][Ng][Na]        Na = unidirectional angles of `distances`
+ *        glrlm [nvox][Ng][Nr][Na]        Na = unidirectional distance-1 angles
+ *        gldm  [nvox][Ng][2*Na+1]        Na = BIdirectional angles of `distances` (_cmatrices.c:790)
+ *        ngtdm [nvox][Ng][3]             columns n_i, s_i, i
+ *      Use rb_generate_angles first to learn Na; `angles` (may be NULL) receives Na x nd ints. */
+int rb_calculate_glcm(const int32_t *image, const uint8_t *mask, const int *size, int nd,
+                      const int *distances, int ndist, int Ng, int force2D, int force2Ddimension,
+                      int kernelRadius, const int *voxels, int nvox, double *glcm, int *angles);
+int rb_calculate_glrlm(const int32_t *image, const uint8_t *mask, const int *size, int nd, int Ng, int Nr,
+                       int force2D, int force2Ddimension, int kernelRadius, const int *voxels, int nvox,
+                       double *glrlm, int *angles);
+int rb_calculate_gldm(const int32_t *image, const uint8_t *mask, const int *size, int nd,
+                      const int *distances, int ndist, int Ng, int alpha, int force2D, int force2Ddimension,
+                      int kernelRadius, const int *voxels, int nvox, double *gldm);
+int rb_calculate_ngtdm(const int32_t *image, const uint8_t *mask, const int *size, int nd,
+                       const int *distances, int ndist, int Ng, int force2D, int force2Ddimension,
+                       int kernelRadius, const int *voxels, int nvox, double *ngtdm);
+/* GLSZM is two-phase like the reference (calculate_glszm finds the zones and the largest zone,
+ * fill_glszm histograms them into [nvox][Ng][max_region]): rb_calculate_glszm returns an opaque
+ * handle and *max_region (0 when there is no zone; allocate with max(1, max_region));
+ * rb_fill_glszm writes the matrix and frees the handle; rb_glszm_release frees it unused. */
+int rb_calculate_glszm(const int32_t *image, const uint8_t *mask, const int *size, int nd, int Ng,
+                       int force2D, int force2Ddimension, int kernelRadius, const int *voxels, int nvox,
+                       int *max_region, void **handle);
+int rb_fill_glszm(void *handle, int Ng, int max_region, double *glszm);
+void rb_glszm_release(void *handle);
+
 #ifdef __cplusplus
 }
 #endif

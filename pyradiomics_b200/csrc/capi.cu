@@ -40,6 +40,15 @@ static bool force_generic() {
   return e && e[0] == '1';
 }
 
+int calculate_matrix_host(int mode, const int32_t* image, const uint8_t* mask, const int* size, int nd,
+                          const int* distances, int ndist, int Ng, int Nr, int alpha, int force2D, int force2Ddimension,
+                          int kernelRadius, const int* voxels, int nvox, double* out_host, int* angles_out, int* na_out);
+int glszm_zones_host(const int32_t* image, const uint8_t* mask, const int* size, int nd, int Ng, int force2D,
+                     int force2Ddimension, int kernelRadius, const int* voxels, int nvox, int* max_region_out,
+                     void** handle_out);
+int glszm_fill_host(void* handle, int Ng, int max_region, double* out_host);
+void glszm_release(void* handle);
+
 static const char* kGlcmNames[] = {"Autocorrelation", "ClusterProminence", "ClusterShade", "ClusterTendency", "Contrast",
   "Correlation", "DifferenceAverage", "DifferenceEntropy", "DifferenceVariance", "Id", "Idm", "Idmn", "Idn", "Imc1", "Imc2",
   "InverseVariance", "JointAverage", "JointEnergy", "JointEntropy", "MCC", "MaximumProbability", "SumAverage", "SumEntropy",
@@ -172,5 +181,38 @@ int rb_voxel_features_host(int cls, const int32_t* image, const uint8_t* mask, i
   cleanup();
   return rc;
 }
+
+int rb_calculate_glcm(const int32_t* image, const uint8_t* mask, const int* size, int nd, const int* distances, int ndist,
+                      int Ng, int force2D, int force2Ddimension, int kernelRadius, const int* voxels, int nvox,
+                      double* glcm, int* angles) {
+  return calculate_matrix_host(0, image, mask, size, nd, distances, ndist, Ng, 0, 0, force2D, force2Ddimension,
+                               kernelRadius, voxels, nvox, glcm, angles, NULL);
+}
+int rb_calculate_glrlm(const int32_t* image, const uint8_t* mask, const int* size, int nd, int Ng, int Nr, int force2D,
+                       int force2Ddimension, int kernelRadius, const int* voxels, int nvox, double* glrlm, int* angles) {
+  return calculate_matrix_host(3, image, mask, size, nd, NULL, 0, Ng, Nr, 0, force2D, force2Ddimension, kernelRadius,
+                               voxels, nvox, glrlm, angles, NULL);
+}
+int rb_calculate_gldm(const int32_t* image, const uint8_t* mask, const int* size, int nd, const int* distances, int ndist,
+                      int Ng, int alpha, int force2D, int force2Ddimension, int kernelRadius, const int* voxels, int nvox,
+                      double* gldm) {
+  return calculate_matrix_host(1, image, mask, size, nd, distances, ndist, Ng, 0, alpha, force2D, force2Ddimension,
+                               kernelRadius, voxels, nvox, gldm, NULL, NULL);
+}
+int rb_calculate_ngtdm(const int32_t* image, const uint8_t* mask, const int* size, int nd, const int* distances,
+                       int ndist, int Ng, int force2D, int force2Ddimension, int kernelRadius, const int* voxels,
+                       int nvox, double* ngtdm) {
+  return calculate_matrix_host(2, image, mask, size, nd, distances, ndist, Ng, 0, 0, force2D, force2Ddimension,
+                               kernelRadius, voxels, nvox, ngtdm, NULL, NULL);
+}
+int rb_calculate_glszm(const int32_t* image, const uint8_t* mask, const int* size, int nd, int Ng, int force2D,
+                       int force2Ddimension, int kernelRadius, const int* voxels, int nvox, int* max_region,
+                       void** handle) {
+  if (!max_region || !handle) return fail(RB_ERR_ARG, "null output pointer");
+  return glszm_zones_host(image, mask, size, nd, Ng, force2D, force2Ddimension, kernelRadius, voxels, nvox, max_region,
+                          handle);
+}
+int rb_fill_glszm(void* handle, int Ng, int max_region, double* glszm) { return glszm_fill_host(handle, Ng, max_region, glszm); }
+void rb_glszm_release(void* handle) { glszm_release(handle); }
 
 }  // extern "C"
