@@ -39,7 +39,14 @@ struct GlcmFastTables {
   uint8_t pA[GF_NA][18], pB[GF_NA][18];      // window positions (z*9+y*3+x) of the two pair ends
   double log2t[GF_LOGT];          // log2(c), log2t[0] = 0 (never used with weight)
   double idm[GF_KT], idmn[GF_KT], id[GF_KT], idn[GF_KT], inv[GF_KT];   // by k = |i-j|
+  double lz0[19], lz1[19];        // Lanczos start vectors (see kLanczosStart0/1)
 };
+
+// Lanczos start vectors: two fixed tables of unstructured components in [0.25, 1.25) (drawn once
+// from a PRNG; anything "generic" works -- arithmetic progressions and Weyl sequences do NOT, they
+// are exactly deficient for symmetric level graphs).
+static const double kLanczosStart0[19] = {0.47733602246716966, 0.56675833970975287, 1.047365457332734, 0.92625467075097456, 0.641109550601909, 0.58281392786638453, 0.84830875358718982, 0.43673418560371335, 0.9227560440146213, 1.1918028652699371, 0.49824571462957101, 1.1988811518333182, 0.91723745310037241, 0.34589793559411208, 0.69183966616781278, 1.1364799193275177, 0.9474534998820221, 0.57647286407011211, 0.9839281633300665};
+static const double kLanczosStart1[19] = {0.47013495554548623, 0.33159456954220812, 0.40989560107504752, 0.59010018495470529, 0.71519315370205094, 0.51642102829077097, 1.065776403424807, 0.44329438928949449, 0.37946907617720027, 0.34166475154493592, 0.84856801366491319, 1.1047419043740012, 0.85162124169371312, 1.1819883611359834, 0.97478136109202007, 1.1105513173932924, 1.1793378015753162, 0.79618600908235304, 1.1876729587677568};
 
 // Host-side construction (Ng = max gray level of the ROI, as used by Idmn / Idn).
 inline void glcm_fast_build_tables(GlcmFastTables& T, int Ng) {
@@ -66,6 +73,7 @@ inline void glcm_fast_build_tables(GlcmFastTables& T, int Ng) {
       for (int t = n; t < 18; t++) { T.pA[slot][t] = 0; T.pB[slot][t] = 0; }
       slot++;
     }
+  for (int i = 0; i < 19; i++) { T.lz0[i] = kLanczosStart0[i]; T.lz1[i] = kLanczosStart1[i]; }
   T.log2t[0] = 0;
   for (int c = 1; c < GF_LOGT; c++) T.log2t[c] = log2((double)c);
   for (int d = 0; d < GF_KT; d++) {
@@ -78,47 +86,106 @@ inline void glcm_fast_build_tables(GlcmFastTables& T, int Ng) {
   }
 }
 
-// second largest |eigenvalue| of the symmetric matrix M(i,j) = n_ij / sqrt(R_i R_j) of one angle
-// whose level graph is connected.  w: 27 window levels, eq: equality masks (stride es).
-template <int NP>
-RB_HDN double glcm_fast_mcc_solve(const uint32_t* eq, int es, const uint8_t* pA, const uint8_t* pB,
-                                  uint32_t valid, uint32_t EA, uint32_t EB, uint32_t all) {
-  // level nodes = distinct levels among the endpoints: representative = lowest position bit
+// MCC eigen-task: second largest |eigenvalue| of the symmetric matrix M(i,j) = n_ij / sqrt(R_i R_j)
+// (normalised co-occurrence of ONE angle whose level graph is connected; its top eigenpair is
+// (1, sqrt(R/S))).  M has <= NP off-diagonal pairs, so instead of a dense O(n^3) reduction it is
+// tridiagonalised by a Lanczos recurrence with SPARSE mat-vecs, started and kept orthogonal to the
+// known top eigenvector; the extreme eigenvalues of the small tridiagonal are then located by
+// Sturm bisection.  Rebuilds everything from the owner's window levels (w, stride ws) and equality
+// masks (eq, stride es), so any thread of the block can execute any voxel's task.
+RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const uint32_t* eq, int es, const GlcmFastTables& T, int s) {
+  const int np = T.np[s];
+  const uint8_t* pA = T.pA[s];
+  const uint8_t* pB = T.pB[s];
+  uint32_t valid = 0, EA = 0, EB = 0;
+  for (int t = 0; t < np; t++)
+    if (w[pA[t] * ws] && w[pB[t] * ws]) { valid |= 1u << t; EA |= 1u << pA[t]; EB |= 1u << pB[t]; }
+  // level nodes: representative = lowest window position holding the level
   uint32_t reps = 0;
-  for (uint32_t m = all; m;) {
-    int v = RB_CTZ(m);
-    uint32_t e = eq[v * es];
+  for (uint32_t m = EA | EB; m;) {
+    const uint32_t e = eq[RB_CTZ(m) * es];
     reps |= 1u << RB_CTZ(e);
     m &= ~e;
   }
   const int n = RB_POPC(reps);
   if (n < 2) return 0.0;
-  double A[19 * 19];
-  double rs[19];
-  for (int i = 0; i < n * n; i++) A[i] = 0;
+  double v1[19], q0[19], q1[19], z[19], ew[18];
+  uint8_t ei[18], ej[18];
+  double S = 0;
   {
     int i = 0;
     for (uint32_t m = reps; m; m &= m - 1, i++) {
-      uint32_t e = eq[RB_CTZ(m) * es];
-      rs[i] = 1.0 / sqrt((double)(RB_POPC(e & EA) + RB_POPC(e & EB)));
+      const uint32_t e = eq[RB_CTZ(m) * es];
+      const double R = (double)(RB_POPC(e & EA) + RB_POPC(e & EB));
+      v1[i] = R; S += R;
     }
   }
-  for (int t = 0; t < NP; t++) {
+  int ne = 0;
+  double tr = 0;   // trace of M (for the n == 2 closed form)
+  for (int t = 0; t < np; t++) {
     if (!(valid >> t & 1u)) continue;
-    int ra = RB_CTZ(eq[pA[t] * es]), rb_ = RB_CTZ(eq[pB[t] * es]);
-    int i = RB_POPC(reps & ((1u << ra) - 1)), j = RB_POPC(reps & ((1u << rb_) - 1));
-    double m = rs[i] * rs[j];
-    A[i * n + j] += m;
-    A[j * n + i] += m;   // i == j: entry (i,i) counted twice, as the symmetrised matrix does
+    const int ra = RB_CTZ(eq[pA[t] * es]), rb_ = RB_CTZ(eq[pB[t] * es]);
+    const int i = RB_POPC(reps & ((1u << ra) - 1)), j = RB_POPC(reps & ((1u << rb_) - 1));
+    ei[ne] = (uint8_t)i; ej[ne] = (uint8_t)j;
+    ew[ne] = 1.0 / sqrt(v1[i] * v1[j]);
+    if (i == j) tr += 2.0 * ew[ne];
+    ne++;
   }
-  double dd[19], ee[19];
-  const double l2 = sym_second_largest_abs(A, n, n, dd, ee);
-  return l2;
+  if (n == 2) return fabs(tr - 1.0);          // eigenvalues are 1 and trace - 1
+  const double invS = 1.0 / S;
+  for (int i = 0; i < n; i++) v1[i] = sqrt(v1[i] * invS);
+  // Lanczos from a fixed pseudo-random start vector projected off v1.  If the recurrence breaks
+  // down before n-1 steps (start vector deficient in some eigenvector, or repeated eigenvalues) the
+  // Ritz values found are still exact eigenvalues; a second start vector covers the deficiency.
+  double best = 0;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    double dot = 0, nrm = 0;
+    for (int i = 0; i < n; i++) {
+      q1[i] = attempt == 0 ? T.lz0[i] : T.lz1[i];
+      dot += q1[i] * v1[i];
+    }
+    for (int i = 0; i < n; i++) { q1[i] -= dot * v1[i]; nrm += q1[i] * q1[i]; q0[i] = 0; }
+    nrm = 1.0 / sqrt(nrm);
+    for (int i = 0; i < n; i++) q1[i] *= nrm;
+    double d[19], e[19];
+    double beta = 0;
+    int m = 0;
+    e[0] = 0;
+    for (int j = 0; j < n - 1; j++) {
+      for (int i = 0; i < n; i++) z[i] = 0;
+      for (int t = 0; t < ne; t++) {
+        const int a = ei[t], b = ej[t];
+        z[a] += ew[t] * q1[b];
+        z[b] += ew[t] * q1[a];
+      }
+      double alpha = 0;
+      for (int i = 0; i < n; i++) alpha += q1[i] * z[i];
+      double dv = 0;
+      for (int i = 0; i < n; i++) { z[i] -= alpha * q1[i] + beta * q0[i]; dv += z[i] * v1[i]; }
+      // re-orthogonalise against the deflated vector and the last two Lanczos vectors
+      double c1 = 0, c0 = 0;
+      for (int i = 0; i < n; i++) { z[i] -= dv * v1[i]; c1 += z[i] * q1[i]; c0 += z[i] * q0[i]; }
+      double nb = 0;
+      for (int i = 0; i < n; i++) { z[i] -= c1 * q1[i] + c0 * q0[i]; nb += z[i] * z[i]; }
+      d[m] = alpha; m++;
+      nb = sqrt(nb);
+      if (nb < 1e-10 || j == n - 2) break;       // invariant subspace reached / basis complete
+      e[m] = nb; beta = nb;
+      const double inb = 1.0 / nb;
+      for (int i = 0; i < n; i++) { q0[i] = q1[i]; q1[i] = z[i] * inb; }
+    }
+    const double hi = tridiag_kth_eigenvalue(d, e, m, m - 1, -1.0 - 1e-6, 1.0 + 1e-6, 34);
+    const double lo = tridiag_kth_eigenvalue(d, e, m, 0, -1.0 - 1e-6, 1.0 + 1e-6, 34);
+    best = fmax(best, fmax(fabs(hi), fabs(lo)));
+    if (m == n - 1) break;
+  }
+  return best;
 }
 
 struct GlcmAcc {
   double sum[GLCM_NF];
   int n_ok, n_imc2;
+  uint32_t tasks;      // bit s set: angle slot s needs an MCC eigen-solve (added to sum[G_MCC] later)
   bool ja_nan;
 };
 
@@ -249,7 +316,8 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
       for (int t = 0; t < NP; t++) if (em[t] & comp) comp |= em[t];
       if (comp == before) break;
     }
-    mcc = (comp == all) ? glcm_fast_mcc_solve<NP>(eq, es, pA, pB, valid, EA, EB, used) : 1.0;
+    if (comp == all) { mcc = 0.0; acc.tasks |= 1u << s; }   // solved later (all lanes busy)
+    else mcc = 1.0;
   }
   f[G_MCC] = mcc;
 #pragma unroll
@@ -258,10 +326,11 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
   if (f[G_Imc2] == f[G_Imc2]) { acc.sum[G_Imc2] += f[G_Imc2]; acc.n_imc2++; }
 }
 
-// all 24 GLCM features of one voxel.  w: the 27 window levels (0 = unmasked / outside);
-// eq: scratch for 27 equality masks with element stride es (shared memory on the device).
-RB_HD void glcm_fast_voxel(const uint8_t* w, int ws, uint32_t* eq, int es, const GlcmFastTables& T,
-                           const VoxParams& P, double* out) {
+// Phase A of one voxel: everything except the MCC eigen-solves.  w: the 27 window levels (0 =
+// unmasked / outside); eq: scratch for 27 equality masks, element stride es (shared memory on the
+// device).  Writes the 24 means (MCC without the pending tasks) and returns the task bitmask.
+RB_HD uint32_t glcm_fast_voxel_phaseA(const uint8_t* w, int ws, uint32_t* eq, int es, const GlcmFastTables& T,
+                                      const VoxParams& P, double* out, int* n_ok_out) {
   uint32_t e[27];
   int wl[27];
 #pragma unroll
@@ -276,15 +345,34 @@ RB_HD void glcm_fast_voxel(const uint8_t* w, int ws, uint32_t* eq, int es, const
   GlcmAcc acc;
 #pragma unroll
   for (int k = 0; k < GLCM_NF; k++) acc.sum[k] = 0;
-  acc.n_ok = 0; acc.n_imc2 = 0; acc.ja_nan = false;
+  acc.n_ok = 0; acc.n_imc2 = 0; acc.ja_nan = false; acc.tasks = 0;
   for (int s = 0; s < 3; s++) glcm_fast_angle<18>(w, ws, eq, es, repmask, T, s, P, acc);
   for (int s = 3; s < 9; s++) glcm_fast_angle<12>(w, ws, eq, es, repmask, T, s, P, acc);
   for (int s = 9; s < 13; s++) glcm_fast_angle<8>(w, ws, eq, es, repmask, T, s, P, acc);
+  *n_ok_out = acc.n_ok;
   const double inv = acc.n_ok ? 1.0 / acc.n_ok : NAN;
 #pragma unroll
   for (int k = 0; k < GLCM_NF; k++) out[k] = acc.n_ok ? acc.sum[k] * inv : NAN;
   out[G_Imc2] = acc.n_imc2 ? acc.sum[G_Imc2] / acc.n_imc2 : NAN;
   if (acc.ja_nan) out[G_JointAverage] = NAN;
+  return acc.tasks;
+}
+
+// finish MCC: add the solved eigen-tasks (in slot order) to the partial mean written by phase A
+RB_HD double glcm_fast_finish_mcc(double partial_mean, int n_ok, uint32_t tasks, const double* solved, int ss) {
+  double add = 0;
+  for (int s = 0; s < GF_NA; s++) if (tasks >> s & 1u) add += solved[s * ss];
+  return n_ok ? partial_mean + add / n_ok : partial_mean;
+}
+
+// single-thread composition (host emulation / reference for the two-phase kernel)
+RB_HD void glcm_fast_voxel(const uint8_t* w, int ws, uint32_t* eq, int es, const GlcmFastTables& T,
+                           const VoxParams& P, double* out) {
+  int n_ok = 0;
+  const uint32_t tasks = glcm_fast_voxel_phaseA(w, ws, eq, es, T, P, out, &n_ok);
+  double solved[GF_NA];
+  for (int s = 0; s < GF_NA; s++) solved[s] = (tasks >> s & 1u) ? glcm_fast_solve_task(w, ws, eq, es, T, s) : 0.0;
+  out[G_MCC] = glcm_fast_finish_mcc(out[G_MCC], n_ok, tasks, solved, 1);
 }
 
 }  // namespace rb

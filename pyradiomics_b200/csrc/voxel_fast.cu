@@ -12,6 +12,15 @@ namespace rb {
 
 constexpr int GF_THREADS = 128;
 
+// Three phases per tile of GF_THREADS consecutive voxels (block-uniform loop):
+//   A  every thread: its voxel's window -> equality masks -> all 13 angles, everything except the
+//      MCC eigen-solves, which are queued as (owner thread, angle slot) tasks in shared memory;
+//   B  the block drains the queue with ALL lanes busy (any thread can rebuild any task from the
+//      owner's window + masks in shared memory) -- eigen-solves are needed by only a few % of the
+//      (voxel, angle) pairs on noisy data but by most on smooth data, so leaving them inline would
+//      idle most lanes of a warp behind one long solve;
+//   C  every thread adds its solved tasks (in slot order: deterministic) and stores 24 coalesced
+//      float64 map values.
 __global__ void __launch_bounds__(GF_THREADS)
 glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ centers,
                  const __grid_constant__ VoxParams P, const GlcmFastTables* __restrict__ Tg,
@@ -19,42 +28,73 @@ glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ ce
   __shared__ GlcmFastTables T;
   __shared__ uint8_t wbuf[27 * GF_THREADS];
   __shared__ uint32_t eqbuf[27 * GF_THREADS];
+  __shared__ double solved[GF_NA * GF_THREADS];
+  __shared__ uint16_t queue[GF_NA * GF_THREADS];
+  __shared__ int qn;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(Tg);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
     for (int i = threadIdx.x; i < (int)(sizeof(GlcmFastTables) / 4); i += GF_THREADS) dst[i] = src[i];
   }
-  __syncthreads();
+  const int tid = threadIdx.x;
   const long long plane = (long long)P.Y * P.X;
   const long long total = (long long)(z1 - z0) * plane;
-  for (long long t = (long long)blockIdx.x * GF_THREADS + threadIdx.x; t < total; t += (long long)gridDim.x * GF_THREADS) {
-    const int z = z0 + (int)(t / plane);
-    const int rem = (int)(t % plane);
-    const int y = rem / P.X, x = rem % P.X;
-    const long long vi = (long long)z * P.sz + (long long)y * P.sy + x;
-    const long long oi = (long long)(z - out_z0) * plane + rem;
-    const bool is_center = centers ? centers[(long long)z * plane + rem] != 0 : lev[vi] != 0;
-    if (!is_center) {
-#pragma unroll
-      for (int k = 0; k < GLCM_NF; k++) out[k * fstride + oi] = P.init_value;
-      continue;
-    }
-    uint8_t* w = &wbuf[threadIdx.x];
-#pragma unroll
-    for (int dz = -1; dz <= 1; dz++)
-#pragma unroll
-      for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-        for (int dx = -1; dx <= 1; dx++) {
-          const int zz = z + dz, yy = y + dy, xx = x + dx;
-          const bool in = zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
-          w[((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)) * GF_THREADS] =
-              in ? lev[vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : (uint8_t)0;
-        }
+  const long long ntiles = (total + GF_THREADS - 1) / GF_THREADS;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (tid == 0) qn = 0;
+    __syncthreads();                       // also covers the table copy on the first pass
+    const long long t = tile * GF_THREADS + tid;
+    const bool live = t < total;
+    int z = 0, rem = 0;
+    long long oi = 0;
+    bool is_center = false;
     double f[GLCM_NF];
-    glcm_fast_voxel(w, GF_THREADS, &eqbuf[threadIdx.x], GF_THREADS, T, P, f);
+    uint32_t tasks = 0;
+    int n_ok = 0;
+    if (live) {
+      z = z0 + (int)(t / plane);
+      rem = (int)(t % plane);
+      const int y = rem / P.X, x = rem % P.X;
+      const long long vi = (long long)z * P.sz + (long long)y * P.sy + x;
+      oi = (long long)(z - out_z0) * plane + rem;
+      is_center = centers ? centers[(long long)z * plane + rem] != 0 : lev[vi] != 0;
+      if (is_center) {
+        uint8_t* w = &wbuf[tid];
 #pragma unroll
-    for (int k = 0; k < GLCM_NF; k++) out[k * fstride + oi] = f[k];
+        for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+          for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+            for (int dx = -1; dx <= 1; dx++) {
+              const int zz = z + dz, yy = y + dy, xx = x + dx;
+              const bool in = zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
+              w[((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)) * GF_THREADS] =
+                  in ? lev[vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : (uint8_t)0;
+            }
+        tasks = glcm_fast_voxel_phaseA(w, GF_THREADS, &eqbuf[tid], GF_THREADS, T, P, f, &n_ok);
+        for (uint32_t m = tasks; m; m &= m - 1) {
+          const int s = __ffs((int)m) - 1;
+          queue[atomicAdd(&qn, 1)] = (uint16_t)(tid | s << 8);
+        }
+      }
+    }
+    __syncthreads();
+    const int nq = qn;
+    for (int k = tid; k < nq; k += GF_THREADS) {
+      const int owner = queue[k] & 0xFF, s = queue[k] >> 8;
+      solved[s * GF_THREADS + owner] = glcm_fast_solve_task(&wbuf[owner], GF_THREADS, &eqbuf[owner], GF_THREADS, T, s);
+    }
+    __syncthreads();
+    if (live) {
+      if (is_center) {
+        f[G_MCC] = glcm_fast_finish_mcc(f[G_MCC], n_ok, tasks, &solved[tid], GF_THREADS);
+#pragma unroll
+        for (int k = 0; k < GLCM_NF; k++) out[k * fstride + oi] = f[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < GLCM_NF; k++) out[k * fstride + oi] = P.init_value;
+      }
+    }
   }
 }
 
@@ -94,7 +134,7 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long long need = (total + GF_THREADS - 1) / GF_THREADS, cap = (long long)sms * 32;
+  long long need = (total + GF_THREADS - 1) / GF_THREADS, cap = (long long)sms * 16;
   const int grid = (int)(need < cap ? need : cap);
   glcm_fast_kernel<<<grid, GF_THREADS, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, z0, z1, out_z0);
   RB_LAUNCH_CHECK();
