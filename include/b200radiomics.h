@@ -146,6 +146,34 @@ int rb_calculate_glszm(const int32_t *image, const uint8_t *mask, const int *siz
 int rb_fill_glszm(void *handle, int Ng, int max_region, double *glszm);
 void rb_glszm_release(void *handle);
 
+/* ---- gray-level discretisation and pre-filters (device pointers, asynchronous) --------------
+ * dtype codes for `image_dev`: 0 int16, 1 int32, 2 float32, 3 float64, 4 uint8, 5 uint16, 6 int64.
+ * rb_minmax_dev: ROI minimum / maximum (mask_dev may be NULL = all voxels) as order-preserving
+ *   int64 keys in keys_dev[0..1] plus the voxel count in keys_dev[2]; initialise keys_dev to
+ *   {INT64_MAX, INT64_MIN, 0}; decode a key k with  bits = k >= 0 ? k : k ^ INT64_MAX.
+ *   Replaces the Python-level min()/max() of getBinEdges (radiomics/imageoperations.py:128-129).
+ * rb_digitize_dev: out[i] = number of edges <= image[i] inside the mask, 0 outside: np.digitize
+ *   on the masked voxels as binImage does (radiomics/imageoperations.py:156-174); comparisons are
+ *   made in float64 against the caller's edges, so bins are bit-identical to NumPy's. */
+int rb_minmax_dev(const void *image_dev, int dtype, const uint8_t *mask_dev, long long nvoxels,
+                  long long *keys_dev, void *stream);
+int rb_digitize_dev(const void *image_dev, int dtype, const uint8_t *mask_dev, long long nvoxels,
+                    const double *edges_dev, int nedges, int32_t *out_dev, void *stream);
+/* One axis (0 = z, 1 = y, 2 = x) of the level-1 stationary wavelet transform with periodic
+ * extension (pywt.swtn(level=1) as called at radiomics/imageoperations.py:935): float64 in, the
+ * low-pass and high-pass outputs in out_lo_dev / out_hi_dev.  dec_lo / dec_hi are HOST arrays of
+ * `flen` decomposition taps.  Odd lengths behave like the reference's wrap-pad-then-crop. */
+int rb_swt_axis_dev(const double *in_dev, int Z, int Y, int X, int axis, const double *dec_lo,
+                    const double *dec_hi, int flen, double *out_lo_dev, double *out_hi_dev, void *stream);
+/* One axis of a 4th-order recursive (IIR) Gaussian / Gaussian-derivative filter, causal +
+ * anti-causal, the building block of ITK's LaplacianRecursiveGaussianImageFilter used at
+ * radiomics/imageoperations.py:824-830.  coef20 (HOST) = N0..N3, D1..D4, M1..M4, BN1..4, BM1..4;
+ * input float32 (in_is_f32) or float64, output float32 = (causal + anticausal) * scale, added to
+ * out_dev when accumulate != 0.  scratch_dev: float64 buffer with as many elements as the volume. */
+int rb_recursive_gaussian_axis_dev(const void *in_dev, int in_is_f32, int Z, int Y, int X, int axis,
+                                   const double *coef20, float *out_dev, double *scratch_dev, double scale,
+                                   int accumulate, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

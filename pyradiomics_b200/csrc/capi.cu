@@ -49,6 +49,14 @@ int glszm_zones_host(const int32_t* image, const uint8_t* mask, const int* size,
 int glszm_fill_host(void* handle, int Ng, int max_region, double* out_host);
 void glszm_release(void* handle);
 
+int minmax_launch(const void* img, int dt, const uint8_t* mask, long long n, long long* keys, cudaStream_t st);
+int digitize_launch(const void* img, int dt, const uint8_t* mask, long long n, const double* edges, int ne, int32_t* out,
+                    cudaStream_t st);
+int swt_axis_launch(const double* in, int Z, int Y, int X, int axis, const double* lo, const double* hi, int F,
+                    double* out_lo, double* out_hi, cudaStream_t st);
+int recursive_gauss_launch(const void* in, int in_is_f32, int Z, int Y, int X, int axis, const double* coef20, float* out,
+                           double* scratch, double scale, int accumulate, cudaStream_t st);
+
 static const char* kGlcmNames[] = {"Autocorrelation", "ClusterProminence", "ClusterShade", "ClusterTendency", "Contrast",
   "Correlation", "DifferenceAverage", "DifferenceEntropy", "DifferenceVariance", "Id", "Idm", "Idmn", "Idn", "Imc1", "Imc2",
   "InverseVariance", "JointAverage", "JointEnergy", "JointEntropy", "MCC", "MaximumProbability", "SumAverage", "SumEntropy",
@@ -214,5 +222,28 @@ int rb_calculate_glszm(const int32_t* image, const uint8_t* mask, const int* siz
 }
 int rb_fill_glszm(void* handle, int Ng, int max_region, double* glszm) { return glszm_fill_host(handle, Ng, max_region, glszm); }
 void rb_glszm_release(void* handle) { glszm_release(handle); }
+
+int rb_minmax_dev(const void* image_dev, int dtype, const uint8_t* mask_dev, long long nvoxels, long long* keys_dev,
+                  void* stream) {
+  if (dtype < 0 || dtype > 6) return fail(RB_ERR_ARG, "unknown dtype code %d", dtype);
+  return minmax_launch(image_dev, dtype, mask_dev, nvoxels, keys_dev, (cudaStream_t)stream);
+}
+int rb_digitize_dev(const void* image_dev, int dtype, const uint8_t* mask_dev, long long nvoxels, const double* edges_dev,
+                    int nedges, int32_t* out_dev, void* stream) {
+  if (dtype < 0 || dtype > 6) return fail(RB_ERR_ARG, "unknown dtype code %d", dtype);
+  if (nedges < 1) return fail(RB_ERR_ARG, "need at least one bin edge");
+  return digitize_launch(image_dev, dtype, mask_dev, nvoxels, edges_dev, nedges, out_dev, (cudaStream_t)stream);
+}
+int rb_swt_axis_dev(const double* in_dev, int Z, int Y, int X, int axis, const double* dec_lo, const double* dec_hi,
+                    int flen, double* out_lo_dev, double* out_hi_dev, void* stream) {
+  if (axis < 0 || axis > 2) return fail(RB_ERR_ARG, "axis must be 0..2");
+  return swt_axis_launch(in_dev, Z, Y, X, axis, dec_lo, dec_hi, flen, out_lo_dev, out_hi_dev, (cudaStream_t)stream);
+}
+int rb_recursive_gaussian_axis_dev(const void* in_dev, int in_is_f32, int Z, int Y, int X, int axis, const double* coef20,
+                                   float* out_dev, double* scratch_dev, double scale, int accumulate, void* stream) {
+  if (axis < 0 || axis > 2) return fail(RB_ERR_ARG, "axis must be 0..2");
+  return recursive_gauss_launch(in_dev, in_is_f32, Z, Y, X, axis, coef20, out_dev, scratch_dev, scale, accumulate,
+                                (cudaStream_t)stream);
+}
 
 }  // extern "C"

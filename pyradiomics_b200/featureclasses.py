@@ -1,0 +1,347 @@
+"""B200 feature-class plugins: the same contract as the reference's ``Radiomics<Class>`` classes
+(reference radiomics/base.py:60-273 and docs/developers.rst:16-64) -- constructor
+``(inputImage, inputMask, **settings)``, ``enableFeatureByName`` / ``enableAllFeatures`` /
+``disableAllFeatures``, ``getFeatureNames``, ``execute()`` returning ``{feature: float}``
+(segment-based) or ``{feature: image}`` (voxel-based), ``_initCalculation`` exposing
+``P_<class>`` -- with the hot path on the GPU:
+
+  * gray-level discretisation: rb_minmax_dev + rb_digitize_dev (imageoperations.binImage)
+  * segment-based: the matrix comes from the CUDA cMatrices drop-in (pyradiomics_b200.cmatrices);
+    the O(Ng^2) scalar formulas stay on the host (_matrix_features.py), as in the reference
+  * voxel-based: ONE fused CUDA kernel per class writes all feature maps (pyradiomics_b200.voxel);
+    no per-voxel matrix is ever materialised and ``voxelBatch`` is not needed.
+
+``install()`` registers them in ``radiomics.getFeatureClasses()`` when pyradiomics is importable.
+"""
+from __future__ import annotations
+
+import inspect
+import logging
+
+import numpy as np
+import torch
+
+from . import _lib, _matrix_features as MF, cmatrices, image as I, imageoperations, voxel
+
+
+def _weights(angles, spacing_zyx, norm, kind):
+    """per-angle weights of weightingNorm (reference glcm.py:160-181 exp(-d^2), glrlm.py:130-150 d)."""
+    if norm is None:
+        return None
+    a = np.abs(np.asarray(angles, float)) * np.asarray(spacing_zyx, float)[-angles.shape[1]:]
+    if norm == "infinity":
+        d = a.max(1)
+    elif norm == "euclidean":
+        d = np.sqrt((a ** 2).sum(1))
+    elif norm == "manhattan":
+        d = a.sum(1)
+    else:
+        if norm != "no_weighting":
+            logging.getLogger("radiomics").warning('weigthing norm "%s" is unknown, W is set to 1', norm)
+        return np.ones(len(angles))
+    return np.exp(-d ** 2) if kind == "glcm" else d
+
+
+class RadiomicsFeaturesBase:
+    """Plugin base; named like the reference's so ``radiomics.getFeatureClasses()``'s MRO-by-name
+    check (reference radiomics/__init__.py:95-99) accepts subclasses."""
+
+    CLASS = None          # "glcm", ...
+    MATRIX_ATTR = None    # "P_glcm", ...
+
+    def __init__(self, inputImage, inputMask, **kwargs):
+        self.logger = logging.getLogger(self.__module__)
+        if inputImage is None or inputMask is None:
+            raise ValueError("Missing input image or mask")
+        self.settings = kwargs
+        self.label = kwargs.get("label", 1)
+        self.voxelBased = kwargs.get("voxelBased", False)
+        self.coefficients = {}
+        self.enabledFeatures = {}
+        self.featureValues = {}
+        self.featureNames = self.getFeatureNames()
+        self.inputImage = inputImage
+        self.inputMask = inputMask
+        self.imageArray = I.as_array(inputImage)
+        labelMask = I.as_array(inputMask) == self.label
+        if self.voxelBased:
+            self.masked = kwargs.get("maskedKernel", True)
+            self.labelledVoxelCoordinates = np.array(np.where(labelMask))
+            self._centerMask = labelMask
+            self.maskArray = labelMask if self.masked else np.ones(self.imageArray.shape, dtype=bool)
+        else:
+            self.maskArray = labelMask
+        setattr(self, self.MATRIX_ATTR, None)
+        self.imageArray = self._applyBinning(self.imageArray)
+
+    # ---- discretisation on the GPU (reference base.py:119-125)
+    def _applyBinning(self, matrix):
+        img_t = imageoperations._to_device(matrix)
+        msk_t = imageoperations._to_device(self.maskArray)
+        lev_t, _ = imageoperations.bin_image_device(img_t, msk_t, **self.settings)
+        Ng = int(lev_t.max().item())
+        packed, presence = voxel.pack_levels(lev_t, msk_t, max(Ng, 1))
+        self._levels_dev = packed
+        gl = (torch.nonzero(presence).flatten() + 1).cpu().numpy().astype(np.int64)
+        self.coefficients["grayLevels"] = gl
+        self.coefficients["Ng"] = int(gl.max())
+        return lev_t.cpu().numpy().astype(np.int64)
+
+    # ---- enabling (reference base.py:127-179)
+    def enableFeatureByName(self, featureName, enable=True):
+        if featureName not in self.featureNames:
+            raise LookupError("Feature not found: " + featureName)
+        if self.featureNames[featureName]:
+            self.logger.warning("Feature %s is deprecated, use with caution!", featureName)
+        self.enabledFeatures[featureName] = enable
+
+    def enableAllFeatures(self):
+        for featureName, is_deprecated in self.featureNames.items():
+            if not is_deprecated:
+                self.enableFeatureByName(featureName, True)
+
+    def disableAllFeatures(self):
+        self.enabledFeatures = {}
+        self.featureValues = {}
+
+    @classmethod
+    def getFeatureNames(cls):
+        return {a[0][3:-12]: getattr(a[1], "_is_deprecated", False) for a in inspect.getmembers(cls)
+                if a[0].startswith("get") and a[0].endswith("FeatureValue")}
+
+    # ---- execution
+    def execute(self):
+        if len(self.enabledFeatures) == 0:
+            self.enableAllFeatures()
+        if self.voxelBased:
+            self._calculateVoxels()
+        else:
+            self._calculateSegment()
+        return self.featureValues
+
+    def _spacing_zyx(self):
+        return tuple(I.spacing_xyz(self.inputImage))[::-1]
+
+    def _voxel_settings(self):
+        kw = dict(self.settings)
+        nd = self.imageArray.ndim
+        if nd == 2 and kw.get("force2D"):
+            kw["force2Ddimension"] = kw.get("force2Ddimension", 0) + 1
+        sp = self._spacing_zyx()
+        kw["spacing_zyx"] = (1.0,) * (3 - nd) + tuple(sp)
+        return _lib.make_settings(self.coefficients["Ng"], len(self.coefficients["grayLevels"]), **kw)
+
+    def _calculateVoxels(self):
+        """ONE fused kernel for the whole class (replaces the voxelBatch loop of base.py:200-245)."""
+        lev = self._levels_dev
+        if lev.ndim == 2:
+            lev = lev[None]
+        centers = None
+        if not self.masked:
+            c = self._centerMask if self._centerMask.ndim == 3 else self._centerMask[None]
+            centers = imageoperations._to_device(c)
+        status = torch.zeros(1, dtype=torch.int32, device=lev.device)
+        maps = voxel.voxel_features(self.CLASS, lev, self._voxel_settings(), centers=centers, status=status)
+        st = int(status.item())
+        if st & 2:
+            raise _lib.B200Error("weighted GLCM entry list overflow")
+        if st & 1:
+            self.logger.warning("MCC eigen-problem too large for the in-kernel solver at some voxels: NaN stored")
+        names = _lib.feature_names(self.CLASS)
+        host = maps.cpu().numpy()
+        for k, name in enumerate(names):
+            if self.enabledFeatures.get(name):
+                arr = host[k] if self.imageArray.ndim == 3 else host[k][0]
+                self.featureValues[name] = I.like(self.inputImage, np.ascontiguousarray(arr))
+
+    def _calculateSegment(self):
+        self._initCalculation()
+        vals = self._segment_features()
+        for feature, enabled in self.enabledFeatures.items():
+            if not enabled:
+                continue
+            if self.featureNames.get(feature):
+                self.logger.debug("Feature %s is deprecated", feature)
+                continue
+            try:
+                self.featureValues[feature] = np.squeeze(np.float64(vals[feature]))
+            except Exception:                                  # per-feature isolation (base.py:271-273)
+                self.logger.error("FAILED: %s", feature, exc_info=True)
+                self.featureValues[feature] = np.nan
+
+    def _initCalculation(self, voxelCoordinates=None):
+        setattr(self, self.MATRIX_ATTR, self._calculateMatrix(voxelCoordinates))
+
+    def _matrix_args(self):
+        return self.settings.get("force2D", False), self.settings.get("force2Ddimension", 0)
+
+    def _batch_args(self, voxelCoordinates):
+        return [self.settings.get("kernelRadius", 1), voxelCoordinates] if voxelCoordinates is not None else []
+
+    def _value(self, name):
+        """single feature (the reference's get<Name>FeatureValue entry points)."""
+        if getattr(self, self.MATRIX_ATTR) is None:
+            self._initCalculation()
+        return np.float64(self._segment_features()[name])
+
+
+def _add_feature_getters(cls, names, deprecated=()):
+    for n in names:
+        def getter(self, _n=n):
+            return self._value(_n)
+        getter.__name__ = f"get{n}FeatureValue"
+        getter.__doc__ = (f"{cls.CLASS.upper()} {n}: same definition as the reference's "
+                          f"Radiomics{cls.CLASS.upper()}.get{n}FeatureValue (see SURVEY.md Appendix C).")
+        setattr(cls, getter.__name__, getter)
+    for n, why in deprecated:
+        def dep(self, _why=why):
+            raise DeprecationWarning(_why)
+        dep.__name__ = f"get{n}FeatureValue"
+        dep.__doc__ = f"DEPRECATED in the reference: {why}"
+        dep._is_deprecated = True
+        setattr(cls, dep.__name__, dep)
+
+
+class RadiomicsGLCM(RadiomicsFeaturesBase):
+    """Gray Level Co-occurrence Matrix features (reference radiomics/glcm.py)."""
+    CLASS, MATRIX_ATTR = "glcm", "P_glcm"
+
+    def __init__(self, inputImage, inputMask, **kwargs):
+        self.symmetricalGLCM = kwargs.get("symmetricalGLCM", True)
+        self.weightingNorm = kwargs.get("weightingNorm")
+        super().__init__(inputImage, inputMask, **kwargs)
+
+    def _calculateMatrix(self, voxelCoordinates=None):
+        f2, f2d = self._matrix_args()
+        P, angles = cmatrices.calculate_glcm(self.imageArray, self.maskArray, np.array(self.settings.get("distances", [1])),
+                                             self.coefficients["Ng"], f2, f2d, *self._batch_args(voxelCoordinates))
+        w = _weights(angles, self._spacing_zyx(), self.weightingNorm, "glcm")
+        return np.stack([MF.glcm_process(P[v], self.coefficients["grayLevels"], self.symmetricalGLCM, w) for v in range(P.shape[0])])
+
+    def _segment_features(self):
+        return MF.glcm_features(self.P_glcm[0], self.coefficients["grayLevels"], self.coefficients["Ng"])
+
+
+_add_feature_getters(RadiomicsGLCM, _lib_names := [
+    "Autocorrelation", "ClusterProminence", "ClusterShade", "ClusterTendency", "Contrast", "Correlation",
+    "DifferenceAverage", "DifferenceEntropy", "DifferenceVariance", "Id", "Idm", "Idmn", "Idn", "Imc1", "Imc2",
+    "InverseVariance", "JointAverage", "JointEnergy", "JointEntropy", "MCC", "MaximumProbability", "SumAverage",
+    "SumEntropy", "SumSquares"],
+    deprecated=[("Dissimilarity", "mathematically equal to Difference Average"),
+                ("Homogeneity1", "mathematically equal to Inverse Difference"),
+                ("Homogeneity2", "mathematically equal to Inverse Difference Moment"),
+                ("SumVariance", "mathematically equal to Cluster Tendency")])
+
+
+class RadiomicsGLRLM(RadiomicsFeaturesBase):
+    """Gray Level Run Length Matrix features (reference radiomics/glrlm.py)."""
+    CLASS, MATRIX_ATTR = "glrlm", "P_glrlm"
+
+    def __init__(self, inputImage, inputMask, **kwargs):
+        self.weightingNorm = kwargs.get("weightingNorm")
+        super().__init__(inputImage, inputMask, **kwargs)
+
+    def _calculateMatrix(self, voxelCoordinates=None):
+        f2, f2d = self._matrix_args()
+        P, angles = cmatrices.calculate_glrlm(self.imageArray, self.maskArray, self.coefficients["Ng"],
+                                              int(np.max(self.imageArray.shape)), f2, f2d, *self._batch_args(voxelCoordinates))
+        w = _weights(angles, self._spacing_zyx(), self.weightingNorm, "glrlm")
+        M, j, Nr = MF.glrlm_process(P[0], self.coefficients["grayLevels"], w)
+        self.coefficients["jvector"], self.coefficients["Nr"] = j, Nr
+        return M[None]
+
+    def _segment_features(self):
+        return MF.glrlm_features(self.P_glrlm[0], self.coefficients["jvector"], self.coefficients["Nr"], self.coefficients["grayLevels"])
+
+
+_add_feature_getters(RadiomicsGLRLM, [
+    "GrayLevelNonUniformity", "GrayLevelNonUniformityNormalized", "GrayLevelVariance", "HighGrayLevelRunEmphasis",
+    "LongRunEmphasis", "LongRunHighGrayLevelEmphasis", "LongRunLowGrayLevelEmphasis", "LowGrayLevelRunEmphasis",
+    "RunEntropy", "RunLengthNonUniformity", "RunLengthNonUniformityNormalized", "RunPercentage", "RunVariance",
+    "ShortRunEmphasis", "ShortRunHighGrayLevelEmphasis", "ShortRunLowGrayLevelEmphasis"])
+
+
+class _SizeMatrixClass(RadiomicsFeaturesBase):
+    NAMES = None
+
+    def _segment_features(self):
+        g = MF.size_matrix_features(getattr(self, self.MATRIX_ATTR)[0], self.coefficients["grayLevels"], self.coefficients["jvector"])
+        return {self.NAMES[k]: v for k, v in g.items() if k in self.NAMES}
+
+
+class RadiomicsGLSZM(_SizeMatrixClass):
+    """Gray Level Size Zone Matrix features (reference radiomics/glszm.py)."""
+    CLASS, MATRIX_ATTR, NAMES = "glszm", "P_glszm", MF.GLSZM_NAMES
+
+    def _calculateMatrix(self, voxelCoordinates=None):
+        f2, f2d = self._matrix_args()
+        P = cmatrices.calculate_glszm(self.imageArray, self.maskArray, self.coefficients["Ng"], int(np.sum(self.maskArray)),
+                                      f2, f2d, *self._batch_args(voxelCoordinates))
+        M, j = MF.size_matrix_process(P[0], self.coefficients["grayLevels"])
+        self.coefficients["jvector"] = j
+        return M[None]
+
+
+_add_feature_getters(RadiomicsGLSZM, sorted(MF.GLSZM_NAMES.values()))
+
+
+class RadiomicsGLDM(_SizeMatrixClass):
+    """Gray Level Dependence Matrix features (reference radiomics/gldm.py)."""
+    CLASS, MATRIX_ATTR, NAMES = "gldm", "P_gldm", MF.GLDM_NAMES
+
+    def __init__(self, inputImage, inputMask, **kwargs):
+        self.gldm_a = kwargs.get("gldm_a", 0)
+        super().__init__(inputImage, inputMask, **kwargs)
+
+    def _calculateMatrix(self, voxelCoordinates=None):
+        f2, f2d = self._matrix_args()
+        P = cmatrices.calculate_gldm(self.imageArray, self.maskArray, np.array(self.settings.get("distances", [1])),
+                                     self.coefficients["Ng"], self.gldm_a, f2, f2d, *self._batch_args(voxelCoordinates))
+        M, j = MF.size_matrix_process(P[0], self.coefficients["grayLevels"])
+        self.coefficients["jvector"] = j
+        return M[None]
+
+
+_add_feature_getters(RadiomicsGLDM, sorted(MF.GLDM_NAMES.values()),
+                     deprecated=[("GrayLevelNonUniformityNormalized", "mathematically equal to First Order - Uniformity"),
+                                 ("DependencePercentage", "always computes 1")])
+
+
+class RadiomicsNGTDM(RadiomicsFeaturesBase):
+    """Neighbouring Gray Tone Difference Matrix features (reference radiomics/ngtdm.py)."""
+    CLASS, MATRIX_ATTR = "ngtdm", "P_ngtdm"
+
+    def _calculateMatrix(self, voxelCoordinates=None):
+        f2, f2d = self._matrix_args()
+        P = cmatrices.calculate_ngtdm(self.imageArray, self.maskArray, np.array(self.settings.get("distances", [1])),
+                                      self.coefficients["Ng"], f2, f2d, *self._batch_args(voxelCoordinates))
+        keep = P[:, :, 0].sum(0) != 0
+        return P[:, keep]
+
+    def _segment_features(self):
+        return MF.ngtdm_features(self.P_ngtdm[0])
+
+
+_add_feature_getters(RadiomicsNGTDM, ["Busyness", "Coarseness", "Complexity", "Contrast", "Strength"])
+
+FEATURE_CLASSES = {"glcm": RadiomicsGLCM, "glrlm": RadiomicsGLRLM, "glszm": RadiomicsGLSZM, "gldm": RadiomicsGLDM,
+                   "ngtdm": RadiomicsNGTDM}
+
+
+def install(radiomics_module=None):
+    """Drop the B200 engine under an importable pyradiomics: the feature classes replace the
+    reference's in ``radiomics.getFeatureClasses()`` and ``cMatrices`` is rebound in every module
+    that captured it at import time."""
+    import importlib
+
+    rad = radiomics_module or importlib.import_module("radiomics")
+    classes = rad.getFeatureClasses()
+    for name, cls in FEATURE_CLASSES.items():
+        classes[name] = cls
+    rad.cMatrices = cmatrices
+    for mod in ("glcm", "glrlm", "glszm", "gldm", "ngtdm", "firstorder"):
+        try:
+            importlib.import_module(f"{rad.__name__}.{mod}").cMatrices = cmatrices
+        except ImportError:
+            pass
+    return classes

@@ -1,0 +1,312 @@
+"""GPU versions of the pyradiomics image operations that sit on the texture hot path
+(reference radiomics/imageoperations.py): gray-level discretisation (getBinEdges / binImage,
+:67-174), the level-1 stationary wavelet decomposition (getWaveletImage / _swt3, :839-970) and the
+Laplacian-of-Gaussian filter (getLoGImage, :756-836).  Same function names, arguments and yielded
+tuples as the reference so they can be dropped into ``radiomics.imageoperations``.
+
+Parity status: binning is bit-identical to NumPy; wavelet and LoG restate PyWavelets'
+and ITK's published algorithms -- neither library is available offline and the reference's own
+tests do not pin them -> "parity unpinned" for those two.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import math
+
+import numpy as np
+import torch
+
+from . import image as I
+from ._lib import check, lib
+
+logger = logging.getLogger("radiomics.imageoperations")
+
+_DT = {np.dtype("int16"): 0, np.dtype("int32"): 1, np.dtype("float32"): 2, np.dtype("float64"): 3,
+       np.dtype("uint8"): 4, np.dtype("uint16"): 5, np.dtype("int64"): 6}
+_TORCH_DT = {torch.int16: 0, torch.int32: 1, torch.float32: 2, torch.float64: 3, torch.uint8: 4, torch.int64: 6}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_device(arr):
+    """NumPy / torch -> contiguous CUDA tensor of a supported dtype (uint16 travels as int32)."""
+    if isinstance(arr, torch.Tensor):
+        t = arr
+        if t.dtype == torch.bool:
+            t = t.to(torch.uint8)
+        if t.dtype not in _TORCH_DT:
+            t = t.to(torch.float64)
+        return t.to(_dev()).contiguous()
+    a = np.asarray(arr)
+    if a.dtype == np.bool_:
+        a = a.view(np.uint8)
+    elif a.dtype == np.uint16:
+        a = a.astype(np.int32)
+    elif a.dtype not in _DT:
+        a = a.astype(np.float64)
+    return torch.from_numpy(np.ascontiguousarray(a)).to(_dev())
+
+
+def _decode_key(k: int) -> float:
+    bits = k if k >= 0 else k ^ 0x7FFFFFFFFFFFFFFF
+    return float(np.array([bits], dtype=np.int64).view(np.float64)[0])
+
+
+def roi_minmax(img_t: torch.Tensor, mask_t: torch.Tensor | None):
+    """(min, max, count) of the ROI, one streaming kernel (replaces builtin min()/max())."""
+    keys = torch.tensor([2 ** 63 - 1, -(2 ** 63), 0], dtype=torch.int64, device=img_t.device)
+    check(lib().rb_minmax_dev(_ptr(img_t), _TORCH_DT[img_t.dtype], _ptr(mask_t), C.c_longlong(img_t.numel()), _ptr(keys),
+                              _stream()), "minmax")
+    k = keys.cpu().tolist()
+    if k[2] == 0:
+        raise ValueError("empty ROI")
+    return _decode_key(k[0]), _decode_key(k[1]), k[2]
+
+
+def _edges_from_minmax(minimum, maximum, is_integer, **kwargs):
+    """reference getBinEdges arithmetic (imageoperations.py:119-149) on the scalars min / max."""
+    binWidth = kwargs.get("binWidth", 25)
+    binCount = kwargs.get("binCount")
+    if is_integer:
+        minimum, maximum = int(minimum), int(maximum)      # integer images keep NumPy integer semantics
+    if binCount is not None:
+        # np.histogram(values, binCount)[1] == np.linspace(min, max, binCount + 1) with the usual
+        # degenerate-range widening; then the last edge + 1
+        lo, hi = float(minimum), float(maximum)
+        if lo == hi:
+            lo, hi = lo - 0.5, hi + 0.5
+        e = np.linspace(lo, hi, int(binCount) + 1, endpoint=True, dtype=np.float64)
+        e[-1] += 1
+        return e
+    lowBound = minimum - (minimum % binWidth)
+    highBound = maximum + 2 * binWidth
+    e = np.arange(lowBound, highBound, binWidth)
+    if len(e) == 1:
+        e = np.array([e[0] - 0.5, e[0] + 0.5])
+    return e
+
+
+def getBinEdges(parameterValues, **kwargs):
+    """reference signature: 1-D array of the segmented voxel values -> bin edges."""
+    t = _to_device(parameterValues).reshape(-1)
+    mn, mx, _ = roi_minmax(t, None)
+    return _edges_from_minmax(mn, mx, not t.dtype.is_floating_point, **kwargs)
+
+
+def bin_image_device(img_t: torch.Tensor, mask_t: torch.Tensor | None, **kwargs):
+    """device tensors in -> (int32 levels tensor (0 outside the mask), edges ndarray)."""
+    mn, mx, _ = roi_minmax(img_t, mask_t)
+    edges = np.ascontiguousarray(_edges_from_minmax(mn, mx, not img_t.dtype.is_floating_point, **kwargs), dtype=np.float64)
+    e_t = torch.from_numpy(edges).to(img_t.device)
+    out = torch.empty(img_t.shape, dtype=torch.int32, device=img_t.device)
+    check(lib().rb_digitize_dev(_ptr(img_t), _TORCH_DT[img_t.dtype], _ptr(mask_t), C.c_longlong(img_t.numel()), _ptr(e_t),
+                                int(edges.size), _ptr(out), _stream()), "digitize")
+    return out, edges
+
+
+def binImage(parameterMatrix, parameterMatrixCoordinates=None, **kwargs):
+    """reference signature (imageoperations.py:156): returns (discretised int array, binEdges).
+    `parameterMatrixCoordinates` is the boolean ROI mask the feature classes pass."""
+    img_t = _to_device(parameterMatrix)
+    mask_t = None
+    if parameterMatrixCoordinates is not None:
+        m = np.asarray(parameterMatrixCoordinates)
+        if m.dtype != np.bool_ or m.shape != tuple(img_t.shape):
+            mm = np.zeros(tuple(img_t.shape), dtype=bool)
+            mm[parameterMatrixCoordinates] = True
+            m = mm
+        mask_t = _to_device(m)
+    out, edges = bin_image_device(img_t, mask_t, **kwargs)
+    return out.cpu().numpy().astype(np.int64), edges
+
+
+# ------------------------------------------------------------------------------------ wavelet
+# decomposition low-pass filters (PyWavelets conventions); dec_hi[k] = (-1)^(k+1) dec_lo[F-1-k]
+_DEC_LO = {
+    "haar": [0.7071067811865476, 0.7071067811865476],
+    "db1": [0.7071067811865476, 0.7071067811865476],
+    "db2": [-0.12940952255126037, 0.2241438680420134, 0.8365163037378079, 0.48296291314453416],
+    "sym2": [-0.12940952255126037, 0.2241438680420134, 0.8365163037378079, 0.48296291314453416],
+    "coif1": [-0.01565572813546454, -0.0727326195128539, 0.38486484686420286, 0.8525720202122554,
+              0.3378976624578092, -0.0727326195128539],
+}
+
+
+def wavelet_filters(name):
+    if not isinstance(name, str):          # a pywt.Wavelet-like object
+        return np.asarray(name.dec_lo, float), np.asarray(name.dec_hi, float)
+    if name not in _DEC_LO:
+        raise ValueError(f"wavelet '{name}' is not in the built-in table {sorted(_DEC_LO)}; pass an object with dec_lo/dec_hi")
+    lo = np.asarray(_DEC_LO[name], float)
+    F = lo.size
+    hi = np.array([(-1) ** (k + 1) * lo[F - 1 - k] for k in range(F)])
+    return lo, hi
+
+
+def swt_level1_device(x: torch.Tensor, axes, lo, hi):
+    """one undecimated level over `axes` (in that order) of a float64 CUDA volume (Z,Y,X):
+    {'aad': tensor, ...} with one letter per axis in `axes` order, like pywt.swtn."""
+    Z, Y, X = x.shape
+    lo = np.ascontiguousarray(lo, dtype=np.float64)
+    hi = np.ascontiguousarray(hi, dtype=np.float64)
+    cur = {"": x}
+    for ax in axes:
+        nxt = {}
+        for key, t in cur.items():
+            a = torch.empty_like(t)
+            d = torch.empty_like(t)
+            check(lib().rb_swt_axis_dev(_ptr(t), Z, Y, X, int(ax), lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p),
+                                        int(lo.size), _ptr(a), _ptr(d), _stream()), "swt")
+            nxt[key + "a"], nxt[key + "d"] = a, d
+        cur = nxt
+    return cur
+
+
+def _swt3(inputImage, axes, **kwargs):
+    wavelet = kwargs.get("wavelet", "coif1")
+    level = kwargs.get("level", 1)
+    start_level = kwargs.get("start_level", 0)
+    lo, hi = wavelet_filters(wavelet)
+    arr = I.as_array(inputImage)
+    nd = arr.ndim
+    data = _to_device(arr).to(torch.float64)
+    if nd == 2:
+        data = data[None]
+    ax3 = [a + (3 - nd) for a in axes]
+    for _ in range(start_level):
+        data = swt_level1_device(data, ax3, lo, hi)["a" * len(axes)]
+    ret = []
+    for _ in range(start_level, start_level + level):
+        dec = swt_level1_device(data, ax3, lo, hi)
+        data = dec["a" * len(axes)]
+        dec_im = {}
+        for name, t in dec.items():
+            if name == "a" * len(axes):
+                continue
+            a = t.cpu().numpy()
+            dec_im[name.replace("a", "L").replace("d", "H")] = I.like(inputImage, a[0] if nd == 2 else a)
+        ret.append(dec_im)
+    a = data.cpu().numpy()
+    return I.like(inputImage, a[0] if nd == 2 else a), ret
+
+
+def getWaveletImage(inputImage, _inputMask, **kwargs):
+    """reference generator (imageoperations.py:839-896): yields (image, name, kwargs)."""
+    Nd = I.as_array(inputImage).ndim
+    axes = list(range(Nd - 1, -1, -1))
+    if kwargs.get("force2D", False):
+        axes.remove(kwargs.get("force2Ddimension", 0))
+    approx, ret = _swt3(inputImage, tuple(axes), **kwargs)
+    for idx, wl in enumerate(ret, start=1):
+        for decompositionName, decompositionImage in wl.items():
+            name = f"wavelet-{decompositionName}" if idx == 1 else f"wavelet{idx}-{decompositionName}"
+            yield decompositionImage, name, kwargs
+    name = f"wavelet-{'L' * len(axes)}" if len(ret) == 1 else f"wavelet{len(ret)}-{'L' * len(axes)}"
+    yield approx, name, kwargs
+
+
+# ------------------------------------------------------------------------------------ LoG
+def recursive_gaussian_coefficients(sigmad: float, order: int, scale_norm: float = 1.0):
+    """Deriche-type 4th-order recursive Gaussian (Farneback-Westin parameterisation) as used by ITK's
+    RecursiveGaussianImageFilter: returns the 20 coefficients N0..3, D1..4, M1..4, BN1..4, BM1..4 for
+    smoothing (order 0) or the second derivative (order 2), sigma in voxels."""
+    A1 = (1.3530, -0.6724, -1.3563); B1 = (1.8151, -3.4327, 5.2318); W1 = 0.6681; L1 = -1.3932
+    A2 = (-0.3531, 0.6724, 0.3446); B2 = (0.0902, 0.6100, -2.2355); W2 = 2.0787; L2 = -1.3732
+    s1, s2 = math.sin(W1 / sigmad), math.sin(W2 / sigmad)
+    c1, c2 = math.cos(W1 / sigmad), math.cos(W2 / sigmad)
+    e1, e2 = math.exp(L1 / sigmad), math.exp(L2 / sigmad)
+    D4 = e1 * e1 * e2 * e2
+    D3 = -2 * c1 * e1 * e2 * e2 - 2 * c2 * e2 * e1 * e1
+    D2 = 4 * c2 * c1 * e1 * e2 + e1 * e1 + e2 * e2
+    D1 = -2 * (e2 * c2 + e1 * c1)
+    SD = 1 + D1 + D2 + D3 + D4
+    DD = D1 + 2 * D2 + 3 * D3 + 4 * D4
+    ED = D1 + 4 * D2 + 9 * D3 + 16 * D4
+
+    def ncoef(a1, b1, a2, b2):
+        N0 = a1 + a2
+        N1 = e2 * (b2 * s2 - (a2 + 2 * a1) * c2) + e1 * (b1 * s1 - (a1 + 2 * a2) * c1)
+        N2 = 2 * e1 * e2 * ((a1 + a2) * c2 * c1 - b1 * c2 * s1 - b2 * c1 * s2) + a2 * e1 * e1 + a1 * e2 * e2
+        N3 = e2 * e1 * e1 * (b2 * s2 - a2 * c2) + e1 * e2 * e2 * (b1 * s1 - a1 * c1)
+        N = np.array([N0, N1, N2, N3])
+        return N, N.sum(), N1 + 2 * N2 + 3 * N3, N1 + 4 * N2 + 9 * N3
+
+    if order == 0:
+        N, SN, _, _ = ncoef(A1[0], B1[0], A2[0], B2[0])
+        alpha0 = 2 * SN / SD - N[0]
+        N = N * (scale_norm / alpha0)
+    elif order == 2:
+        N0s, SN0, DN0, EN0 = ncoef(A1[0], B1[0], A2[0], B2[0])
+        N2s, SN2, DN2, EN2 = ncoef(A1[2], B1[2], A2[2], B2[2])
+        beta = -(2 * SN2 - SD * N2s[0]) / (2 * SN0 - SD * N0s[0])
+        N = N2s + beta * N0s
+        SN, DN, EN = SN2 + beta * SN0, DN2 + beta * DN0, EN2 + beta * EN0
+        alpha2 = (EN * SD * SD - ED * SN * SD - 2 * DN * DD * SD + 2 * DD * DD * SN) / (SD * SD * SD)
+        N = N * (scale_norm / alpha2)
+    else:
+        raise ValueError("order must be 0 or 2")
+    D = np.array([D1, D2, D3, D4])
+    M = np.array([N[1] - D1 * N[0], N[2] - D2 * N[0], N[3] - D3 * N[0], -D4 * N[0]])   # symmetric kernel
+    SNn, SM = N.sum(), M.sum()
+    BN = D * SNn / SD
+    BM = D * SM / SD
+    return np.concatenate([N, D, M, BN, BM]).astype(np.float64)
+
+
+def log_filter_device(x: torch.Tensor, sigma_mm: float, spacing_zyx):
+    """sigma^2-normalised Laplacian of Gaussian of a CUDA volume (Z,Y,X) -> float32 tensor."""
+    Z, Y, X = x.shape
+    src = x.to(torch.float32) if x.dtype != torch.float64 else x
+    scratch = torch.empty((Z, Y, X), dtype=torch.float64, device=x.device)
+    out = torch.zeros((Z, Y, X), dtype=torch.float32, device=x.device)
+    tmp = [torch.empty((Z, Y, X), dtype=torch.float32, device=x.device) for _ in range(2)]
+    for d in range(3):
+        cur, cur_f32 = src, src.dtype == torch.float32
+        k = 0
+        for e in range(3):
+            if e == d:
+                continue
+            coef = recursive_gaussian_coefficients(sigma_mm / spacing_zyx[e], 0)
+            check(lib().rb_recursive_gaussian_axis_dev(_ptr(cur), int(cur_f32), Z, Y, X, e, coef.ctypes.data_as(C.c_void_p),
+                                                       _ptr(tmp[k]), _ptr(scratch), C.c_double(1.0), 0, _stream()), "LoG")
+            cur, cur_f32 = tmp[k], True
+            k ^= 1
+        sd = sigma_mm / spacing_zyx[d]
+        coef = recursive_gaussian_coefficients(sd, 2)
+        # sigma^2 * d^2/dx^2 in physical units = (sigma/spacing)^2 * d^2/di^2
+        check(lib().rb_recursive_gaussian_axis_dev(_ptr(cur), 1, Z, Y, X, d, coef.ctypes.data_as(C.c_void_p), _ptr(out),
+                                                   _ptr(scratch), C.c_double(sd * sd), 1, _stream()), "LoG")
+    return out
+
+
+def getLoGImage(inputImage, _inputMask, **kwargs):
+    """reference generator (imageoperations.py:756-836)."""
+    arr = I.as_array(inputImage)
+    size = np.array(arr.shape[::-1])
+    spacing = np.array(I.spacing_xyz(inputImage), dtype=float)
+    if arr.ndim != 3 or np.min(size) < 4:
+        logger.warning("Image too small to apply LoG filter, size: %s", size)
+        return
+    x = _to_device(arr)
+    for sigma in kwargs.get("sigma", []):
+        if sigma > 0.0:
+            if np.all(size >= np.ceil(sigma / spacing) + 1):
+                out = log_filter_device(x, float(sigma), tuple(spacing[::-1]))
+                name = f"log-sigma-{str(sigma).replace('.', '-')}-mm-3D"
+                yield I.like(inputImage, out.cpu().numpy()), name, kwargs
+            else:
+                logger.warning("applyLoG: sigma(%s)/spacing(%s) + 1 must be greater than the size(%s) of the inputImage",
+                               sigma, spacing, size)
+        else:
+            logger.warning("applyLoG: sigma must be greater than 0.0: %s", sigma)

@@ -1,0 +1,165 @@
+"""GPU tests of the plugin layer: gray-level discretisation (bit-identical to NumPy), the feature
+classes against the reference's baseline CSV values / golden matrices / voxel maps, and the
+wavelet + LoG kernels against their numpy restatements and mathematical properties."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import filters_np as FN
+import pipeline as PL
+from helpers import GOLDEN, assert_maps_close, ref_map, voxel_goldens
+from pyradiomics_b200 import featureclasses as FC, image as I, imageoperations as IO
+
+pytestmark = pytest.mark.gpu
+CASES = ["brain1", "brain2", "breast1", "lung1", "lung2"]
+
+
+@pytest.fixture(scope="module")
+def seg():
+    return np.load(os.path.join(GOLDEN, "segment_cases.npz")), json.load(open(os.path.join(GOLDEN, "segment_expect.json")))
+
+
+# ------------------------------------------------------------------------------ discretisation
+@pytest.mark.parametrize("kw", [dict(binWidth=25), dict(binWidth=3.5), dict(binCount=64), dict(binWidth=5000)])
+@pytest.mark.parametrize("dtype", ["int16", "float64", "float32"])
+def test_binning_is_bit_identical_to_numpy(kw, dtype):
+    rng = np.random.default_rng(4)
+    img = (rng.normal(300, 180, (9, 20, 21))).astype(dtype)
+    if dtype == "int16":
+        img[0, 0, :4] = [75, 100, 125, -25]            # values exactly on bin edges
+    msk = rng.random(img.shape) > 0.3
+    got, edges = IO.binImage(img, msk, **kw)
+    ref, redges, _, _ = PL.bin_image(img, msk, kw.get("binWidth", 25), kw.get("binCount"))
+    assert np.array_equal(np.asarray(edges, float), np.asarray(redges, float))
+    assert np.array_equal(got, ref)
+    assert np.array_equal(IO.getBinEdges(img[msk], **kw), redges)
+
+
+def test_binning_flat_region():
+    img = np.full((4, 5, 6), 50, np.int16)
+    got, edges = IO.binImage(img, np.ones(img.shape, bool), binWidth=25)
+    assert list(edges) == [50, 75, 100] or len(edges) >= 2
+    assert (got == 1).all()
+
+
+# ------------------------------------------------------------------------------ feature classes
+@pytest.mark.parametrize("cname", list(FC.FEATURE_CLASSES))
+def test_segment_features_match_reference_baseline(seg, cname):
+    """reference tests/test_features.py: every baseline column whose settings touch only the hot path"""
+    cases, expect = seg
+    for test, e in expect[cname].items():
+        c = e["case"]
+        img = I.ArrayImage(cases[c + "_image"], cases[c + "_spacing"])
+        msk = I.ArrayImage(cases[c + "_mask"].astype(np.uint8), cases[c + "_spacing"])
+        obj = FC.FEATURE_CLASSES[cname](img, msk, **e["settings"])
+        got = obj.execute()
+        assert set(got) == set(e["features"]), (set(got) ^ set(e["features"]))
+        for f, v in e["features"].items():
+            assert abs(float(got[f]) - v) <= 1e-7 * max(abs(v), 1e-12), (cname, test, f, float(got[f]), v)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_processed_matrices_match_reference_golden(seg, case):
+    """reference tests/test_matrices.py:35-65: P_<class> after _initCalculation()"""
+    cases, _ = seg
+    img = I.ArrayImage(cases[case + "_image"], cases[case + "_spacing"])
+    msk = I.ArrayImage(cases[case + "_mask"].astype(np.uint8), cases[case + "_spacing"])
+    for cname, cls in FC.FEATURE_CLASSES.items():
+        obj = cls(img, msk, binWidth=25)
+        obj._initCalculation()
+        P = getattr(obj, "P_" + cname)[0]
+        assert np.abs(P - cases[f"{case}_{cname}_P"]).max() < 1e-3
+
+
+@pytest.mark.parametrize("name,z,kw", voxel_goldens(), ids=[g[0] for g in voxel_goldens()])
+def test_voxel_based_plugin_maps_match_reference(name, z, kw):
+    sp = z["spacing"]
+    img = I.ArrayImage(z["image"], sp)
+    msk = I.ArrayImage(z["mask"].astype(np.uint8), sp)
+    for cname, cls in FC.FEATURE_CLASSES.items():
+        got = cls(img, msk, voxelBased=True, **kw).execute()
+        for f, im in got.items():
+            assert_maps_close(I.as_array(im), ref_map(z, cname, f), f"{name}/{cname}/{f}")
+
+
+def test_unmasked_kernel_and_feature_selection():
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 200, (6, 7, 8)).astype(np.int16)
+    msk = np.zeros(img.shape, np.uint8)
+    msk[2:5, 2:6, 1:7] = 1
+    obj = FC.RadiomicsGLDM(img, msk, voxelBased=True, maskedKernel=False, binWidth=25, initValue=-1)
+    obj.enableFeatureByName("DependenceEntropy")
+    got = obj.execute()
+    assert list(got) == ["DependenceEntropy"]
+    m = I.as_array(got["DependenceEntropy"])
+    assert (m[msk == 0] == -1).all()
+    ref = PL.extract("gldm", img, msk.astype(bool), voxelBased=True, binWidth=25, maskedKernel=False)
+    assert np.allclose(m[msk == 1], ref["DependenceEntropy"], rtol=1e-9)
+    with pytest.raises(LookupError):
+        obj.enableFeatureByName("NoSuchFeature")
+
+
+def test_every_feature_has_a_docstring():
+    """reference tests/test_docstrings.py"""
+    for cls in FC.FEATURE_CLASSES.values():
+        for name in cls.getFeatureNames():
+            assert getattr(cls, f"get{name}FeatureValue").__doc__
+
+
+# ------------------------------------------------------------------------------ wavelet
+@pytest.mark.parametrize("shape", [(8, 10, 12), (7, 9, 12), (5, 6)])
+def test_wavelet_matches_restatement_and_is_an_isometry(shape):
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=shape)
+    lo, hi = IO.wavelet_filters("coif1")
+    assert abs(lo.sum() - np.sqrt(2)) < 1e-12 and abs((lo ** 2).sum() - 1) < 1e-12 and abs(hi.sum()) < 1e-12
+    got = {n: I.as_array(im) for im, n, _ in IO.getWaveletImage(I.ArrayImage(x), None)}
+    nd = len(shape)
+    ref = FN.swtn_level1(x, lo, hi, tuple(range(nd - 1, -1, -1)))
+    assert len(got) == 2 ** nd
+    for key, arr in ref.items():
+        name = "wavelet-" + key.replace("a", "L").replace("d", "H")
+        assert np.allclose(got[name], arr, rtol=1e-12, atol=1e-12), name
+    if all(s % 2 == 0 for s in shape):
+        # undecimated transform with these sqrt(2)-normalised filters: sum of band energies = 2^nd * |x|^2
+        e = sum((v ** 2).sum() for v in got.values())
+        assert abs(e - 2 ** nd * (x ** 2).sum()) < 1e-9 * e
+    const = {n: I.as_array(im) for im, n, _ in IO.getWaveletImage(I.ArrayImage(np.full(shape, 3.0)), None)}
+    for n, v in const.items():
+        target = 3.0 * np.sqrt(2) ** nd if n == "wavelet-" + "L" * nd else 0.0
+        assert np.allclose(v, target, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------ LoG
+def test_log_matches_restatement_and_analytic_gaussian_laplace():
+    import scipy.ndimage as ndi
+    rng = np.random.default_rng(3)
+    x = ndi.gaussian_filter(rng.normal(size=(40, 44, 48)), 2.0) * 100
+    sp = (1.0, 1.0, 1.0)
+    for sigma in (1.0, 2.0, 3.0):
+        out = [I.as_array(im) for im, n, _ in IO.getLoGImage(I.ArrayImage(x.astype(np.float32), sp), None, sigma=[sigma])][0]
+        assert out.dtype == np.float32
+        # restatement (float64 recursion of the same coefficients)
+        ref = np.zeros(x.shape)
+        xf = x.astype(np.float32).astype(np.float64)
+        for d in range(3):
+            cur = xf
+            for e in range(3):
+                if e != d:
+                    cur = FN.recursive_gaussian_axis(cur, IO.recursive_gaussian_coefficients(sigma, 0), e).astype(np.float32).astype(np.float64)
+            ref += (FN.recursive_gaussian_axis(cur, IO.recursive_gaussian_coefficients(sigma, 2), d) * sigma ** 2).astype(np.float32)
+        assert np.allclose(out, ref, rtol=2e-4, atol=2e-4 * np.abs(ref).max())
+        # analytic sigma^2-normalised Gaussian Laplacian (truncated FIR), interior only
+        ana = ndi.gaussian_laplace(x, sigma, mode="nearest", truncate=6.0) * sigma ** 2
+        c = slice(12, -12)
+        err = np.abs(out[c, c, c] - ana[c, c, c]).max() / np.abs(ana[c, c, c]).max()
+        assert err < 0.03, (sigma, err)
+
+
+def test_log_size_guards():
+    assert list(IO.getLoGImage(I.ArrayImage(np.zeros((3, 8, 8))), None, sigma=[1.0])) == []
+    names = [n for _, n, _ in IO.getLoGImage(I.ArrayImage(np.zeros((8, 8, 8), np.float32)), None, sigma=[1.5, -1])]
+    assert names == ["log-sigma-1-5-mm-3D"]
