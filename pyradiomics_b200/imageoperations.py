@@ -74,19 +74,25 @@ def roi_minmax(img_t: torch.Tensor, mask_t: torch.Tensor | None):
     return _decode_key(k[0]), _decode_key(k[1]), k[2]
 
 
-def _edges_from_minmax(minimum, maximum, is_integer, **kwargs):
-    """reference getBinEdges arithmetic (imageoperations.py:119-149) on the scalars min / max."""
+_NP_OF_TORCH = {torch.int16: np.int16, torch.int32: np.int32, torch.float32: np.float32, torch.float64: np.float64,
+                torch.uint8: np.uint8, torch.int64: np.int64}
+
+
+def _edges_from_minmax(minimum, maximum, np_type, **kwargs):
+    """reference getBinEdges arithmetic (imageoperations.py:119-149) on the scalars min / max, carried
+    out in the image's own NumPy scalar type so that float32 / integer inputs round exactly as
+    `min(values) - (min(values) % binWidth)`, np.arange and np.histogram do in the reference."""
     binWidth = kwargs.get("binWidth", 25)
     binCount = kwargs.get("binCount")
-    if is_integer:
-        minimum, maximum = int(minimum), int(maximum)      # integer images keep NumPy integer semantics
+    minimum, maximum = np_type(minimum), np_type(maximum)
     if binCount is not None:
-        # np.histogram(values, binCount)[1] == np.linspace(min, max, binCount + 1) with the usual
-        # degenerate-range widening; then the last edge + 1
-        lo, hi = float(minimum), float(maximum)
+        # np.histogram(values, binCount)[1]: linspace(min, max, binCount + 1) in the result type of
+        # the data (float64 for integers), degenerate range widened by +-0.5; then last edge + 1
+        et = np.dtype(np.float64) if np.issubdtype(np_type, np.integer) else np.dtype(np_type)
+        lo, hi = et.type(minimum), et.type(maximum)
         if lo == hi:
-            lo, hi = lo - 0.5, hi + 0.5
-        e = np.linspace(lo, hi, int(binCount) + 1, endpoint=True, dtype=np.float64)
+            lo, hi = lo - et.type(0.5), hi + et.type(0.5)
+        e = np.linspace(lo, hi, int(binCount) + 1, endpoint=True, dtype=et)
         e[-1] += 1
         return e
     lowBound = minimum - (minimum % binWidth)
@@ -101,18 +107,19 @@ def getBinEdges(parameterValues, **kwargs):
     """reference signature: 1-D array of the segmented voxel values -> bin edges."""
     t = _to_device(parameterValues).reshape(-1)
     mn, mx, _ = roi_minmax(t, None)
-    return _edges_from_minmax(mn, mx, not t.dtype.is_floating_point, **kwargs)
+    return _edges_from_minmax(mn, mx, _NP_OF_TORCH[t.dtype], **kwargs)
 
 
 def bin_image_device(img_t: torch.Tensor, mask_t: torch.Tensor | None, **kwargs):
     """device tensors in -> (int32 levels tensor (0 outside the mask), edges ndarray)."""
     mn, mx, _ = roi_minmax(img_t, mask_t)
-    edges = np.ascontiguousarray(_edges_from_minmax(mn, mx, not img_t.dtype.is_floating_point, **kwargs), dtype=np.float64)
+    edges_native = _edges_from_minmax(mn, mx, _NP_OF_TORCH[img_t.dtype], **kwargs)
+    edges = np.ascontiguousarray(edges_native, dtype=np.float64)
     e_t = torch.from_numpy(edges).to(img_t.device)
     out = torch.empty(img_t.shape, dtype=torch.int32, device=img_t.device)
     check(lib().rb_digitize_dev(_ptr(img_t), _TORCH_DT[img_t.dtype], _ptr(mask_t), C.c_longlong(img_t.numel()), _ptr(e_t),
                                 int(edges.size), _ptr(out), _stream()), "digitize")
-    return out, edges
+    return out, edges_native
 
 
 def binImage(parameterMatrix, parameterMatrixCoordinates=None, **kwargs):
