@@ -31,6 +31,7 @@ namespace rb {
 constexpr int GF_NA = 13;
 constexpr int GF_LOGT = 40;       // log2 table covers 0..2*18+1
 constexpr int GF_KT = 256;        // |a-b| tables
+constexpr int GF_BISECT = 27;     // Sturm bisection steps: interval 2/2^27 = 1.5e-8 (tolerance budget 1e-5)
 
 struct GlcmFastTables {
   // per angle (in processing order: 3 axis, 6 face-diagonal, 4 body-diagonal)
@@ -174,8 +175,25 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const uint32_t* eq,
       const double inb = 1.0 / nb;
       for (int i = 0; i < n; i++) { q0[i] = q1[i]; q1[i] = z[i] * inb; }
     }
-    const double hi = tridiag_kth_eigenvalue(d, e, m, m - 1, -1.0 - 1e-6, 1.0 + 1e-6, 34);
-    const double lo = tridiag_kth_eigenvalue(d, e, m, 0, -1.0 - 1e-6, 1.0 + 1e-6, 34);
+    // largest eigenvalue of the deflated tridiagonal, then the most negative one only if some
+    // eigenvalue lies below -|hi| (one extra Sturm evaluation decides)
+    const double hi = tridiag_kth_eigenvalue(d, e, m, m - 1, -1.0 - 1e-6, 1.0 + 1e-6, GF_BISECT);
+    double lo = 0;
+    {
+      const double x = -fabs(hi) - 1e-7;
+      // count(x) > 0  <=>  the smallest eigenvalue is <= x  <=>  bisection of k=0 on [-1-d, x] is needed
+      double pm2 = 1.0, pm1 = d[0] - x; int cnt = pm1 <= 0;
+      for (int i = 1; i < m && !cnt; i++) {
+        const double e2 = e[i] * e[i];
+        if (e2 == 0) { pm2 = 1.0; pm1 = d[i] - x; cnt += pm1 <= 0; continue; }
+        const double p = (d[i] - x) * pm1 - e2 * pm2;
+        const bool neg_prev = pm1 < 0 || (pm1 == 0 && pm2 > 0);
+        const bool neg_cur = p < 0 || (p == 0 && !neg_prev);
+        cnt += neg_cur != neg_prev;
+        pm2 = pm1; pm1 = p;
+      }
+      if (cnt) lo = tridiag_kth_eigenvalue(d, e, m, 0, -1.0 - 1e-6, x, GF_BISECT);
+    }
     best = fmax(best, fmax(fabs(hi), fabs(lo)));
     if (m == n - 1) break;
   }
@@ -316,8 +334,33 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
       for (int t = 0; t < NP; t++) if (em[t] & comp) comp |= em[t];
       if (comp == before) break;
     }
-    if (comp == all) { mcc = 0.0; acc.tasks |= 1u << s; }   // solved later (all lanes busy)
-    else mcc = 1.0;
+    if (comp != all) mcc = 1.0;
+    else {
+      // connected.  A bipartite level graph (no level paired with itself, no odd cycle) has the
+      // eigenvalue -1 next to +1 -> second largest |eigenvalue| = 1 without a solve.
+      bool bip = key2[0] != 0;               // smallest |a-b| == 0  <=>  some pair (a,a): self-loop
+      if (bip) {
+        uint32_t A = 0, B = 0;
+#pragma unroll
+        for (int t = 0; t < NP; t++) if (!A && (valid >> t & 1u)) { A = eq[pA[t] * es]; B = eq[pB[t] * es]; }
+        for (int sweep = 0; sweep < NP; sweep++) {
+          const uint32_t a0 = A, b0 = B;
+#pragma unroll
+          for (int t = 0; t < NP; t++) {
+            if (!(valid >> t & 1u)) continue;
+            const uint32_t a = eq[pA[t] * es], b = eq[pB[t] * es];
+            if (a & A) B |= b;
+            if (a & B) A |= b;
+            if (b & A) B |= a;
+            if (b & B) A |= a;
+          }
+          if (A == a0 && B == b0) break;
+        }
+        bip = (A & B) == 0;
+      }
+      if (bip) mcc = 1.0;
+      else { mcc = 0.0; acc.tasks |= 1u << s; }   // eigen-solve queued (phase B)
+    }
   }
   f[G_MCC] = mcc;
 #pragma unroll

@@ -6,95 +6,126 @@
 
 #include "common.cuh"
 #include "glcm_fast.cuh"
+#include "glrlm_fast.cuh"
 #include "host_common.hpp"
 
 namespace rb {
 
 constexpr int GF_THREADS = 128;
 
-// Three phases per tile of GF_THREADS consecutive voxels (block-uniform loop):
-//   A  every thread: its voxel's window -> equality masks -> all 13 angles, everything except the
-//      MCC eigen-solves, which are queued as (owner thread, angle slot) tasks in shared memory;
-//   B  the block drains the queue with ALL lanes busy (any thread can rebuild any task from the
-//      owner's window + masks in shared memory) -- eigen-solves are needed by only a few % of the
-//      (voxel, angle) pairs on noisy data but by most on smooth data, so leaving them inline would
-//      idle most lanes of a warp behind one long solve;
-//   C  every thread adds its solved tasks (in slot order: deterministic) and stores 24 coalesced
-//      float64 map values.
+// Two kernels per chunk of planes:
+//   A  one thread per centre voxel: window -> equality masks -> all 13 angles, every feature except
+//      the MCC eigen-solves; voxels that need solves append one 16-byte entry (voxel, slot mask,
+//      n_ok) to a device queue.  No local memory, no block barriers.
+//   B  one thread per queue entry: reloads the voxel's 27 levels, solves its queued angles with the
+//      sparse Lanczos + Sturm solver (glcm_fast_solve_task) and adds them to the voxel's MCC in slot
+//      order (single writer per voxel: deterministic).  Eigen-solves are needed by a few % of the
+//      (voxel, angle) pairs on noisy data and by most on smooth data; left inline they idle most
+//      lanes of a warp behind one long solve and force 255 registers on every thread.
+struct GlcmTask {
+  long long vi;        // linear index of the voxel in the level volume
+  uint32_t mask;       // angle slots to solve
+  int n_ok;            // number of non-empty angles (the nanmean denominator)
+};
+
 __global__ void __launch_bounds__(GF_THREADS)
 glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ centers,
                  const __grid_constant__ VoxParams P, const GlcmFastTables* __restrict__ Tg,
-                 double* __restrict__ out, long long fstride, int z0, int z1, int out_z0) {
+                 double* __restrict__ out, long long fstride, int z0, int z1, int out_z0,
+                 GlcmTask* __restrict__ queue, unsigned* __restrict__ qcount) {
   __shared__ GlcmFastTables T;
   __shared__ uint8_t wbuf[27 * GF_THREADS];
   __shared__ uint32_t eqbuf[27 * GF_THREADS];
-  __shared__ double solved[GF_NA * GF_THREADS];
-  __shared__ uint16_t queue[GF_NA * GF_THREADS];
-  __shared__ int qn;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(Tg);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
     for (int i = threadIdx.x; i < (int)(sizeof(GlcmFastTables) / 4); i += GF_THREADS) dst[i] = src[i];
   }
+  __syncthreads();
   const int tid = threadIdx.x;
   const long long plane = (long long)P.Y * P.X;
   const long long total = (long long)(z1 - z0) * plane;
-  const long long ntiles = (total + GF_THREADS - 1) / GF_THREADS;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    if (tid == 0) qn = 0;
-    __syncthreads();                       // also covers the table copy on the first pass
-    const long long t = tile * GF_THREADS + tid;
-    const bool live = t < total;
-    int z = 0, rem = 0;
-    long long oi = 0;
-    bool is_center = false;
-    double f[GLCM_NF];
-    uint32_t tasks = 0;
-    int n_ok = 0;
-    if (live) {
-      z = z0 + (int)(t / plane);
-      rem = (int)(t % plane);
-      const int y = rem / P.X, x = rem % P.X;
-      const long long vi = (long long)z * P.sz + (long long)y * P.sy + x;
-      oi = (long long)(z - out_z0) * plane + rem;
-      is_center = centers ? centers[(long long)z * plane + rem] != 0 : lev[vi] != 0;
-      if (is_center) {
-        uint8_t* w = &wbuf[tid];
+  for (long long t = (long long)blockIdx.x * GF_THREADS + tid; t < total; t += (long long)gridDim.x * GF_THREADS) {
+    const int z = z0 + (int)(t / plane);
+    const int rem = (int)(t % plane);
+    const int y = rem / P.X, x = rem % P.X;
+    const long long vi = (long long)z * P.sz + (long long)y * P.sy + x;
+    const long long oi = (long long)(z - out_z0) * plane + rem;
+    const bool is_center = centers ? centers[(long long)z * plane + rem] != 0 : lev[vi] != 0;
+    if (!is_center) {
 #pragma unroll
-        for (int dz = -1; dz <= 1; dz++)
+      for (int k = 0; k < GLCM_NF; k++) out[k * fstride + oi] = P.init_value;
+      continue;
+    }
+    uint8_t* w = &wbuf[tid];
 #pragma unroll
-          for (int dy = -1; dy <= 1; dy++)
+    for (int dz = -1; dz <= 1; dz++)
 #pragma unroll
-            for (int dx = -1; dx <= 1; dx++) {
-              const int zz = z + dz, yy = y + dy, xx = x + dx;
-              const bool in = zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
-              w[((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)) * GF_THREADS] =
-                  in ? lev[vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : (uint8_t)0;
-            }
-        tasks = glcm_fast_voxel_phaseA(w, GF_THREADS, &eqbuf[tid], GF_THREADS, T, P, f, &n_ok);
-        for (uint32_t m = tasks; m; m &= m - 1) {
-          const int s = __ffs((int)m) - 1;
-          queue[atomicAdd(&qn, 1)] = (uint16_t)(tid | s << 8);
+      for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) {
+          const int zz = z + dz, yy = y + dy, xx = x + dx;
+          const bool in = zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
+          w[((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)) * GF_THREADS] =
+              in ? lev[vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : (uint8_t)0;
         }
-      }
-    }
-    __syncthreads();
-    const int nq = qn;
-    for (int k = tid; k < nq; k += GF_THREADS) {
-      const int owner = queue[k] & 0xFF, s = queue[k] >> 8;
-      solved[s * GF_THREADS + owner] = glcm_fast_solve_task(&wbuf[owner], GF_THREADS, &eqbuf[owner], GF_THREADS, T, s);
-    }
-    __syncthreads();
-    if (live) {
-      if (is_center) {
-        f[G_MCC] = glcm_fast_finish_mcc(f[G_MCC], n_ok, tasks, &solved[tid], GF_THREADS);
+    double f[GLCM_NF];
+    int n_ok = 0;
+    const uint32_t tasks = glcm_fast_voxel_phaseA(w, GF_THREADS, &eqbuf[tid], GF_THREADS, T, P, f, &n_ok);
 #pragma unroll
-        for (int k = 0; k < GLCM_NF; k++) out[k * fstride + oi] = f[k];
-      } else {
-#pragma unroll
-        for (int k = 0; k < GLCM_NF; k++) out[k * fstride + oi] = P.init_value;
-      }
+    for (int k = 0; k < GLCM_NF; k++) out[k * fstride + oi] = f[k];
+    if (tasks) {
+      const unsigned q = atomicAdd(qcount, 1u);
+      GlcmTask e;
+      e.vi = vi; e.mask = tasks; e.n_ok = n_ok;
+      queue[q] = e;
     }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ VoxParams P,
+                       const GlcmFastTables* __restrict__ Tg, double* __restrict__ mcc_map /* out + G_MCC*fstride */,
+                       int out_z0, const GlcmTask* __restrict__ queue, const unsigned* __restrict__ qcount) {
+  __shared__ GlcmFastTables T;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(Tg);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
+    for (int i = threadIdx.x; i < (int)(sizeof(GlcmFastTables) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const unsigned n = *qcount;
+  const long long plane = (long long)P.Y * P.X;
+  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const GlcmTask e = queue[k];
+    const int z = (int)(e.vi / P.sz), rem = (int)(e.vi % P.sz), y = rem / (int)P.sy, x = rem % (int)P.sy;
+    uint8_t w[27];
+    uint32_t eq[27];
+    {
+      int wl[27];
+      int p = 0;
+#pragma unroll
+      for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+          for (int dx = -1; dx <= 1; dx++, p++) {
+            const int zz = z + dz, yy = y + dy, xx = x + dx;
+            const bool in = zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
+            wl[p] = in ? lev[e.vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : 0;
+          }
+      uint32_t m[27];
+      RB_EQMASKS_27(wl, m);
+#pragma unroll
+      for (int q = 0; q < 27; q++) { w[q] = (uint8_t)wl[q]; eq[q] = m[q]; }
+    }
+    double add = 0;
+    for (uint32_t mk = e.mask; mk; mk &= mk - 1) {
+      const int s = __ffs((int)mk) - 1;
+      add += glcm_fast_solve_task(w, 1, eq, 1, T, s);
+    }
+    const long long oi = (long long)(z - out_z0) * plane + (long long)y * P.X + x;
+    mcc_map[oi] += add / e.n_ok;
   }
 }
 
@@ -125,18 +156,135 @@ bool glcm_fast_applicable(int cls, int level_bytes, const VoxParams& P) {
          !P.weighted && P.Ng <= 255;
 }
 
+// per (device, stream) task queue, grown on demand
+struct GlcmQueue { GlcmTask* q = nullptr; unsigned* count = nullptr; size_t cap = 0; };
+static GlcmQueue* glcm_queue(cudaStream_t st, size_t need) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, GlcmQueue> cache;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  GlcmQueue& Q = cache[{dev, st}];
+  if (!Q.count && cudaMalloc(&Q.count, sizeof(unsigned)) != cudaSuccess) return nullptr;
+  if (Q.cap < need) {
+    if (Q.q) { cudaStreamSynchronize(st); cudaFree(Q.q); Q.q = nullptr; Q.cap = 0; }
+    if (cudaMalloc(&Q.q, need * sizeof(GlcmTask)) != cudaSuccess) return nullptr;
+    Q.cap = need;
+  }
+  return &Q;
+}
+
 int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P, double* out, long long fstride,
                      int z0, int z1, int out_z0, cudaStream_t st) {
   const GlcmFastTables* T = glcm_fast_tables_dev(P.Ng);
   if (!T) return fail(RB_ERR_CUDA, "could not build the GLCM table block on the device");
+  const long long plane = (long long)P.Y * P.X;
+  if ((long long)(z1 - z0) * plane <= 0) return RB_OK;
+  if (P.sy != P.X || P.sz != plane) return fail(RB_ERR_ARG, "GLCM fast path expects a contiguous level volume");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // chunk of planes whose worst-case queue (one entry per voxel) stays <= 16 Mi entries (256 MB)
+  const long long max_entries = 16ll << 20;
+  int zchunk = (int)(max_entries / plane);
+  if (zchunk < 1) zchunk = 1;
+  if (zchunk > z1 - z0) zchunk = z1 - z0;
+  GlcmQueue* Q = glcm_queue(st, (size_t)zchunk * plane);
+  if (!Q) return fail(RB_ERR_NOMEM, "could not allocate the GLCM eigen-task queue");
+  for (int za = z0; za < z1; za += zchunk) {
+    const int zb = za + zchunk < z1 ? za + zchunk : z1;
+    const long long total = (long long)(zb - za) * plane;
+    RB_CUDA(cudaMemsetAsync(Q->count, 0, sizeof(unsigned), st));
+    long long need = (total + GF_THREADS - 1) / GF_THREADS, cap = (long long)sms * 16;
+    const int grid = (int)(need < cap ? need : cap);
+    glcm_fast_kernel<<<grid, GF_THREADS, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
+    RB_LAUNCH_CHECK();
+    glcm_fast_solve_kernel<<<sms * 8, 128, 0, st>>>((const uint8_t*)lev, P, T, out + (long long)G_MCC * fstride, out_z0, Q->q, Q->count);
+    RB_LAUNCH_CHECK();
+  }
+  return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------- GLRLM
+__global__ void __launch_bounds__(128)
+glrlm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ centers,
+                  const __grid_constant__ VoxParams P, const GlrlmFastTables* __restrict__ Tg,
+                  double* __restrict__ out, long long fstride, int z0, int z1, int out_z0) {
+  __shared__ GlrlmFastTables T;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(Tg);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
+    for (int i = threadIdx.x; i < (int)(sizeof(GlrlmFastTables) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const long long plane = (long long)P.Y * P.X;
+  const long long total = (long long)(z1 - z0) * plane;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int z = z0 + (int)(t / plane);
+    const int rem = (int)(t % plane);
+    const int y = rem / P.X, x = rem % P.X;
+    const long long vi = (long long)z * P.sz + (long long)y * P.sy + x;
+    const long long oi = (long long)(z - out_z0) * plane + rem;
+    const bool is_center = centers ? centers[(long long)z * plane + rem] != 0 : lev[vi] != 0;
+    if (!is_center) {
+#pragma unroll
+      for (int k = 0; k < GLRLM_NF; k++) out[k * fstride + oi] = P.init_value;
+      continue;
+    }
+    int wl[27];
+    {
+      int p = 0;
+#pragma unroll
+      for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+          for (int dx = -1; dx <= 1; dx++, p++) {
+            const int zz = z + dz, yy = y + dy, xx = x + dx;
+            const bool in = zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
+            wl[p] = in ? lev[vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : 0;
+          }
+    }
+    double f[GLRLM_NF];
+    glrlm_fast_voxel(wl, T, f);
+#pragma unroll
+    for (int k = 0; k < GLRLM_NF; k++) out[k * fstride + oi] = f[k];
+  }
+}
+
+static const GlrlmFastTables* glrlm_fast_tables_dev() {
+  static std::mutex mu;
+  static std::map<int, GlrlmFastTables*> cache;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(dev);
+  if (it != cache.end()) return it->second;
+  GlrlmFastTables* h = new GlrlmFastTables;
+  memset(h, 0, sizeof *h);
+  glrlm_fast_build_tables(*h);
+  GlrlmFastTables* d = nullptr;
+  if (cudaMalloc(&d, sizeof *h) != cudaSuccess || cudaMemcpy(d, h, sizeof *h, cudaMemcpyHostToDevice) != cudaSuccess) { delete h; return nullptr; }
+  delete h;
+  cache[dev] = d;
+  return d;
+}
+
+bool glrlm_fast_applicable(int cls, int level_bytes, const VoxParams& P) {
+  return cls == C_GLRLM && level_bytes == 1 && P.rz == 1 && P.ry == 1 && P.rx == 1 && P.na == 13 && !P.weighted && P.Ng <= 255;
+}
+
+int glrlm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P, double* out, long long fstride,
+                      int z0, int z1, int out_z0, cudaStream_t st) {
+  const GlrlmFastTables* T = glrlm_fast_tables_dev();
+  if (!T) return fail(RB_ERR_CUDA, "could not build the GLRLM table block on the device");
   const long long total = (long long)(z1 - z0) * P.Y * P.X;
   if (total <= 0) return RB_OK;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long long need = (total + GF_THREADS - 1) / GF_THREADS, cap = (long long)sms * 16;
-  const int grid = (int)(need < cap ? need : cap);
-  glcm_fast_kernel<<<grid, GF_THREADS, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, z0, z1, out_z0);
+  long long need = (total + 127) / 128, cap = (long long)sms * 32;
+  glrlm_fast_kernel<<<(int)(need < cap ? need : cap), 128, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, z0, z1, out_z0);
   RB_LAUNCH_CHECK();
   return RB_OK;
 }

@@ -79,3 +79,26 @@ extern "C" double emul_glcm_solve_window(const uint8_t* w, int slot, int Ng) {
   delete T;
   return r;
 }
+
+#include "../../pyradiomics_b200/csrc/glrlm_fast.cuh"
+// GLRLM fast path (r=1, 13 angles, unweighted, 8-bit levels) on the host
+extern "C" int emul_glrlm_fast(const uint16_t* lev, int Z, int Y, int X, const VoxSettings* s, double* out) {
+  VoxParams P;
+  int rc = fill_vox_params(C_GLRLM, Z, Y, X, *s, P);
+  if (rc) return rc;
+  if (P.na != 13 || P.rz != 1 || P.ry != 1 || P.rx != 1 || P.weighted || s->Ng > 255) return -5;
+  GlrlmFastTables* T = new GlrlmFastTables;
+  glrlm_fast_build_tables(*T);
+  const long long nvox = (long long)Z * Y * X;
+  for (int z = 0; z < Z; z++) for (int y = 0; y < Y; y++) for (int x = 0; x < X; x++) {
+    long long i = ((long long)z * Y + y) * X + x;
+    if (!lev[i]) { for (int k = 0; k < GLRLM_NF; k++) out[k * nvox + i] = P.init_value; continue; }
+    uint16_t w16[27]; int wl[27]; double f[GLRLM_NF];
+    load_window<uint16_t>(lev, P, z, y, x, w16);
+    for (int k = 0; k < 27; k++) wl[k] = w16[k];
+    glrlm_fast_voxel(wl, *T, f);
+    for (int k = 0; k < GLRLM_NF; k++) out[k * nvox + i] = f[k];
+  }
+  delete T;
+  return 0;
+}

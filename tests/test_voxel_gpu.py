@@ -111,3 +111,16 @@ def test_glcm_fast_path_equals_generic_kernel(kind, monkeypatch):
         # MCC / Imc2 of near-degenerate angles are rounding noise in every implementation
         atol = 1e-6 if f in ("MCC", "Imc2", "Imc1") else 1e-9
         assert np.allclose(fast[k], gen[k], rtol=1e-7, atol=atol, equal_nan=True), f
+
+
+@pytest.mark.parametrize("kind", ["uniform", "smooth"])
+def test_glrlm_fast_path_equals_generic_kernel(kind, monkeypatch):
+    lev = torch.as_tensor(_random_volume(kind, (40, 40, 40), 3).astype(np.uint8)).cuda()
+    lev[5:9, 3:30, 7] = 0
+    lev[20, :, :] = 0
+    s = _lib.make_settings(32, 32)
+    fast = voxel.voxel_features("glrlm", lev, s).cpu().numpy()
+    monkeypatch.setenv("B200_RADIOMICS_FORCE_GENERIC", "1")
+    gen = voxel.voxel_features("glrlm", lev, s).cpu().numpy()
+    monkeypatch.delenv("B200_RADIOMICS_FORCE_GENERIC")
+    assert np.allclose(fast, gen, rtol=1e-10, atol=1e-12, equal_nan=True)
