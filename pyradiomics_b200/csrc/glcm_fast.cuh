@@ -92,45 +92,34 @@ inline void glcm_fast_build_tables(GlcmFastTables& T, int Ng) {
 // (1, sqrt(R/S))).  M has <= NP off-diagonal pairs, so instead of a dense O(n^3) reduction it is
 // tridiagonalised by a Lanczos recurrence with SPARSE mat-vecs, started and kept orthogonal to the
 // known top eigenvector; the extreme eigenvalues of the small tridiagonal are then located by
-// Sturm bisection.  Rebuilds everything from the owner's window levels (w, stride ws) and equality
-// masks (eq, stride es), so any thread of the block can execute any voxel's task.
-RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const uint32_t* eq, int es, const GlcmFastTables& T, int s) {
+// Sturm bisection.  Rebuilds everything from the voxel's 27 window levels (w, stride ws) alone, so
+// any thread can execute any voxel's task.
+RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const GlcmFastTables& T, int s) {
   const int np = T.np[s];
   const uint8_t* pA = T.pA[s];
   const uint8_t* pB = T.pB[s];
-  uint32_t valid = 0, EA = 0, EB = 0;
-  for (int t = 0; t < np; t++)
-    if (w[pA[t] * ws] && w[pB[t] * ws]) { valid |= 1u << t; EA |= 1u << pA[t]; EB |= 1u << pB[t]; }
-  // level nodes: representative = lowest window position holding the level
-  uint32_t reps = 0;
-  for (uint32_t m = EA | EB; m;) {
-    const uint32_t e = eq[RB_CTZ(m) * es];
-    reps |= 1u << RB_CTZ(e);
-    m &= ~e;
-  }
-  const int n = RB_POPC(reps);
-  if (n < 2) return 0.0;
+  // level nodes (<= 19 for a connected graph with <= 18 edges), R = endpoint multiplicity = row sum
   double v1[19], q0[19], q1[19], z[19], ew[18];
-  uint8_t ei[18], ej[18];
-  double S = 0;
-  {
-    int i = 0;
-    for (uint32_t m = reps; m; m &= m - 1, i++) {
-      const uint32_t e = eq[RB_CTZ(m) * es];
-      const double R = (double)(RB_POPC(e & EA) + RB_POPC(e & EB));
-      v1[i] = R; S += R;
-    }
-  }
-  int ne = 0;
-  double tr = 0;   // trace of M (for the n == 2 closed form)
+  uint8_t nodelev[19], ei[18], ej[18];
+  int n = 0, ne = 0;
+  for (int i = 0; i < 19; i++) v1[i] = 0;
   for (int t = 0; t < np; t++) {
-    if (!(valid >> t & 1u)) continue;
-    const int ra = RB_CTZ(eq[pA[t] * es]), rb_ = RB_CTZ(eq[pB[t] * es]);
-    const int i = RB_POPC(reps & ((1u << ra) - 1)), j = RB_POPC(reps & ((1u << rb_) - 1));
-    ei[ne] = (uint8_t)i; ej[ne] = (uint8_t)j;
-    ew[ne] = 1.0 / sqrt(v1[i] * v1[j]);
-    if (i == j) tr += 2.0 * ew[ne];
-    ne++;
+    const uint8_t a = w[pA[t] * ws], b = w[pB[t] * ws];
+    if (!a || !b) continue;
+    int i = 0, j = 0;
+    for (; i < n; i++) if (nodelev[i] == a) break;
+    if (i == n) { if (n >= 19) return 1.0; nodelev[n++] = a; }
+    for (; j < n; j++) if (nodelev[j] == b) break;
+    if (j == n) { if (n >= 19) return 1.0; nodelev[n++] = b; }
+    ei[ne] = (uint8_t)i; ej[ne] = (uint8_t)j; ne++;
+    v1[i] += 1.0; v1[j] += 1.0;
+  }
+  if (n < 2) return 0.0;
+  double S = 0, tr = 0;
+  for (int i = 0; i < n; i++) S += v1[i];
+  for (int t = 0; t < ne; t++) {
+    ew[t] = 1.0 / sqrt(v1[ei[t]] * v1[ej[t]]);
+    if (ei[t] == ej[t]) tr += 2.0 * ew[t];      // trace of M
   }
   if (n == 2) return fabs(tr - 1.0);          // eigenvalues are 1 and trace - 1
   const double invS = 1.0 / S;
@@ -174,6 +163,16 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const uint32_t* eq,
       e[m] = nb; beta = nb;
       const double inb = 1.0 / nb;
       for (int i = 0; i < n; i++) { q0[i] = q1[i]; q1[i] = z[i] * inb; }
+    }
+    if (m <= 2) {                             // closed forms for 1x1 / 2x2
+      double hi2 = d[0], lo2 = d[0];
+      if (m == 2) {
+        const double mid = 0.5 * (d[0] + d[1]), hd = 0.5 * (d[0] - d[1]), rad = sqrt(hd * hd + e[1] * e[1]);
+        hi2 = mid + rad; lo2 = mid - rad;
+      }
+      best = fmax(best, fmax(fabs(hi2), fabs(lo2)));
+      if (m == n - 1) break;
+      continue;
     }
     // largest eigenvalue of the deflated tridiagonal, then the most negative one only if some
     // eigenvalue lies below -|hi| (one extra Sturm evaluation decides)
@@ -414,7 +413,7 @@ RB_HD void glcm_fast_voxel(const uint8_t* w, int ws, uint32_t* eq, int es, const
   int n_ok = 0;
   const uint32_t tasks = glcm_fast_voxel_phaseA(w, ws, eq, es, T, P, out, &n_ok);
   double solved[GF_NA];
-  for (int s = 0; s < GF_NA; s++) solved[s] = (tasks >> s & 1u) ? glcm_fast_solve_task(w, ws, eq, es, T, s) : 0.0;
+  for (int s = 0; s < GF_NA; s++) solved[s] = (tasks >> s & 1u) ? glcm_fast_solve_task(w, ws, T, s) : 0.0;
   out[G_MCC] = glcm_fast_finish_mcc(out[G_MCC], n_ok, tasks, solved, 1);
 }
 

@@ -1,6 +1,8 @@
 // Fast fused voxel-based kernels for the headline configuration (kernelRadius 1, 3-D,
 // distances [1], 8-bit levels).  One thread per centre voxel, consecutive threads = consecutive
 // x so the 24 float64 map stores of a warp are 256-byte coalesced segments.
+#include <stdlib.h>
+
 #include <map>
 #include <mutex>
 
@@ -15,20 +17,25 @@ constexpr int GF_THREADS = 128;
 
 // Two kernels per chunk of planes:
 //   A  one thread per centre voxel: window -> equality masks -> all 13 angles, every feature except
-//      the MCC eigen-solves; voxels that need solves append one 16-byte entry (voxel, slot mask,
-//      n_ok) to a device queue.  No local memory, no block barriers.
-//   B  one thread per queue entry: reloads the voxel's 27 levels, solves its queued angles with the
-//      sparse Lanczos + Sturm solver (glcm_fast_solve_task) and adds them to the voxel's MCC in slot
-//      order (single writer per voxel: deterministic).  Eigen-solves are needed by a few % of the
+//      the MCC eigen-solves; a voxel that needs k solves reserves k CONSECUTIVE 16-byte queue entries
+//      (voxel, angle slot, n_ok).  No local memory, no block barriers.
+//   B  one thread per queue entry (= one eigen-task): reloads the voxel's 27 levels and runs the
+//      sparse Lanczos + Sturm solver (glcm_fast_solve_task); result to res[k].
+//   C  one thread per voxel-with-tasks adds its results in slot order to the voxel's MCC (single
+//      writer, fixed order: deterministic).  Eigen-solves are needed by a few % of the
 //      (voxel, angle) pairs on noisy data and by most on smooth data; left inline they idle most
 //      lanes of a warp behind one long solve and force 255 registers on every thread.
 struct GlcmTask {
   long long vi;        // linear index of the voxel in the level volume
-  uint32_t mask;       // angle slots to solve
-  int n_ok;            // number of non-empty angles (the nanmean denominator)
+  uint8_t slot;        // angle slot to solve
+  uint8_t n_ok;        // number of non-empty angles of the voxel (the nanmean denominator)
+  uint8_t count;       // > 0 on the first task of a voxel: how many consecutive entries belong to it
+  uint8_t pad;
+  float unused;
 };
 
-__global__ void __launch_bounds__(GF_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(GF_THREADS, MINB)
 glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ centers,
                  const __grid_constant__ VoxParams P, const GlcmFastTables* __restrict__ Tg,
                  double* __restrict__ out, long long fstride, int z0, int z1, int out_z0,
@@ -75,18 +82,24 @@ glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ ce
 #pragma unroll
     for (int k = 0; k < GLCM_NF; k++) out[k * fstride + oi] = f[k];
     if (tasks) {
-      const unsigned q = atomicAdd(qcount, 1u);
-      GlcmTask e;
-      e.vi = vi; e.mask = tasks; e.n_ok = n_ok;
-      queue[q] = e;
+      const int k = __popc(tasks);
+      unsigned q = atomicAdd(qcount, (unsigned)k);
+      bool first = true;
+      for (uint32_t m = tasks; m; m &= m - 1, q++) {
+        GlcmTask e;
+        e.vi = vi; e.slot = (uint8_t)(__ffs((int)m) - 1); e.n_ok = (uint8_t)n_ok; e.count = first ? (uint8_t)k : 0;
+        e.pad = 0; e.unused = 0.f;
+        queue[q] = e;
+        first = false;
+      }
     }
   }
 }
 
 __global__ void __launch_bounds__(128)
 glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ VoxParams P,
-                       const GlcmFastTables* __restrict__ Tg, double* __restrict__ mcc_map /* out + G_MCC*fstride */,
-                       int out_z0, const GlcmTask* __restrict__ queue, const unsigned* __restrict__ qcount) {
+                       const GlcmFastTables* __restrict__ Tg, const GlcmTask* __restrict__ queue,
+                       const unsigned* __restrict__ qcount, double* __restrict__ res) {
   __shared__ GlcmFastTables T;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(Tg);
@@ -95,36 +108,39 @@ glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ 
   }
   __syncthreads();
   const unsigned n = *qcount;
-  const long long plane = (long long)P.Y * P.X;
   for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const GlcmTask e = queue[k];
     const int z = (int)(e.vi / P.sz), rem = (int)(e.vi % P.sz), y = rem / (int)P.sy, x = rem % (int)P.sy;
     uint8_t w[27];
-    uint32_t eq[27];
-    {
-      int wl[27];
-      int p = 0;
+    int p = 0;
 #pragma unroll
-      for (int dz = -1; dz <= 1; dz++)
+    for (int dz = -1; dz <= 1; dz++)
 #pragma unroll
-        for (int dy = -1; dy <= 1; dy++)
+      for (int dy = -1; dy <= 1; dy++)
 #pragma unroll
-          for (int dx = -1; dx <= 1; dx++, p++) {
-            const int zz = z + dz, yy = y + dy, xx = x + dx;
-            const bool in = zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
-            wl[p] = in ? lev[e.vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : 0;
-          }
-      uint32_t m[27];
-      RB_EQMASKS_27(wl, m);
-#pragma unroll
-      for (int q = 0; q < 27; q++) { w[q] = (uint8_t)wl[q]; eq[q] = m[q]; }
-    }
+        for (int dx = -1; dx <= 1; dx++, p++) {
+          const int zz = z + dz, yy = y + dy, xx = x + dx;
+          const bool in = zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
+          w[p] = in ? lev[e.vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : (uint8_t)0;
+        }
+    res[k] = glcm_fast_solve_task(w, 1, T, e.slot);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+glcm_fast_finish_kernel(const __grid_constant__ VoxParams P, const GlcmTask* __restrict__ queue,
+                        const unsigned* __restrict__ qcount, const double* __restrict__ res,
+                        double* __restrict__ mcc_map /* out + G_MCC*fstride */, int out_z0) {
+  const unsigned n = *qcount;
+  const long long plane = (long long)P.Y * P.X;
+  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const GlcmTask e = queue[k];
+    if (!e.count) continue;
     double add = 0;
-    for (uint32_t mk = e.mask; mk; mk &= mk - 1) {
-      const int s = __ffs((int)mk) - 1;
-      add += glcm_fast_solve_task(w, 1, eq, 1, T, s);
-    }
-    const long long oi = (long long)(z - out_z0) * plane + (long long)y * P.X + x;
+    for (int j = 0; j < e.count; j++) add += res[k + j];
+    const int z = (int)(e.vi / P.sz);
+    const long long oi = e.vi - (long long)out_z0 * plane;   // contiguous volume: vi = z*plane + rem
+    (void)z;
     mcc_map[oi] += add / e.n_ok;
   }
 }
@@ -157,7 +173,7 @@ bool glcm_fast_applicable(int cls, int level_bytes, const VoxParams& P) {
 }
 
 // per (device, stream) task queue, grown on demand
-struct GlcmQueue { GlcmTask* q = nullptr; unsigned* count = nullptr; size_t cap = 0; };
+struct GlcmQueue { GlcmTask* q = nullptr; double* res = nullptr; unsigned* count = nullptr; size_t cap = 0; };
 static GlcmQueue* glcm_queue(cudaStream_t st, size_t need) {
   static std::mutex mu;
   static std::map<std::pair<int, cudaStream_t>, GlcmQueue> cache;
@@ -167,8 +183,9 @@ static GlcmQueue* glcm_queue(cudaStream_t st, size_t need) {
   GlcmQueue& Q = cache[{dev, st}];
   if (!Q.count && cudaMalloc(&Q.count, sizeof(unsigned)) != cudaSuccess) return nullptr;
   if (Q.cap < need) {
-    if (Q.q) { cudaStreamSynchronize(st); cudaFree(Q.q); Q.q = nullptr; Q.cap = 0; }
+    if (Q.q) { cudaStreamSynchronize(st); cudaFree(Q.q); cudaFree(Q.res); Q.q = nullptr; Q.res = nullptr; Q.cap = 0; }
     if (cudaMalloc(&Q.q, need * sizeof(GlcmTask)) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&Q.res, need * sizeof(double)) != cudaSuccess) { cudaFree(Q.q); Q.q = nullptr; return nullptr; }
     Q.cap = need;
   }
   return &Q;
@@ -184,12 +201,13 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // chunk of planes whose worst-case queue (one entry per voxel) stays <= 16 Mi entries (256 MB)
-  const long long max_entries = 16ll << 20;
-  int zchunk = (int)(max_entries / plane);
+  // chunk of planes whose worst-case queue (13 eigen-tasks per voxel) stays <= 48 Mi entries
+  // (768 MB of tasks + 384 MB of results)
+  const long long max_entries = 48ll << 20;
+  int zchunk = (int)(max_entries / (plane * GF_NA));
   if (zchunk < 1) zchunk = 1;
   if (zchunk > z1 - z0) zchunk = z1 - z0;
-  GlcmQueue* Q = glcm_queue(st, (size_t)zchunk * plane);
+  GlcmQueue* Q = glcm_queue(st, (size_t)zchunk * plane * GF_NA);
   if (!Q) return fail(RB_ERR_NOMEM, "could not allocate the GLCM eigen-task queue");
   for (int za = z0; za < z1; za += zchunk) {
     const int zb = za + zchunk < z1 ? za + zchunk : z1;
@@ -197,9 +215,14 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
     RB_CUDA(cudaMemsetAsync(Q->count, 0, sizeof(unsigned), st));
     long long need = (total + GF_THREADS - 1) / GF_THREADS, cap = (long long)sms * 16;
     const int grid = (int)(need < cap ? need : cap);
-    glcm_fast_kernel<<<grid, GF_THREADS, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
+    static const int minb = getenv("B200_GLCM_MINB") ? atoi(getenv("B200_GLCM_MINB")) : 2;
+    if (minb >= 4) glcm_fast_kernel<4><<<grid, GF_THREADS, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
+    else if (minb == 3) glcm_fast_kernel<3><<<grid, GF_THREADS, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
+    else glcm_fast_kernel<2><<<grid, GF_THREADS, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
     RB_LAUNCH_CHECK();
-    glcm_fast_solve_kernel<<<sms * 8, 128, 0, st>>>((const uint8_t*)lev, P, T, out + (long long)G_MCC * fstride, out_z0, Q->q, Q->count);
+    glcm_fast_solve_kernel<<<sms * 8, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
+    RB_LAUNCH_CHECK();
+    glcm_fast_finish_kernel<<<sms * 8, 256, 0, st>>>(P, Q->q, Q->count, Q->res, out + (long long)G_MCC * fstride, out_z0);
     RB_LAUNCH_CHECK();
   }
   return RB_OK;

@@ -73,9 +73,7 @@ extern "C" int emul_glcm_fast(const uint16_t* lev, int Z, int Y, int X, const Vo
 extern "C" double emul_glcm_solve_window(const uint8_t* w, int slot, int Ng) {
   GlcmFastTables* T = new GlcmFastTables;
   glcm_fast_build_tables(*T, Ng);
-  uint32_t e[27];
-  for (int p = 0; p < 27; p++) { e[p] = 0; for (int q = 0; q < 27; q++) if (w[p] && w[p] == w[q]) e[p] |= 1u << q; }
-  double r = glcm_fast_solve_task(w, 1, e, 1, *T, slot);
+  double r = glcm_fast_solve_task(w, 1, *T, slot);
   delete T;
   return r;
 }
