@@ -216,6 +216,8 @@ def run_b200(args):
             for c in CLASSES}
     ev = {c: [] for c in CLASSES}
     launches = 0
+    zchunk = max(1, (48 << 20) // (Z * Z * 13))
+    glcm_chunks = -(-nz // zchunk)
 
     def step(record):
         nonlocal launches
@@ -223,13 +225,14 @@ def run_b200(args):
         buf = slab.buf
         alive = voxel.glcm_alive_angles(buf, settings)
         alive = D.allreduce_alive(alive, dev)
-        launches += 1
+        launches += 1                                  # glcm_alive_kernel
         for c in CLASSES:
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             voxel.voxel_features(c, buf, settings, z0=r, z1=r + nz, out=outs[c], out_z0=r, alive=alive)
-            launches += 1
+            # GLCM = (features, eigen-solve, finish) kernels per plane chunk of the task queue
+            launches += 3 * glcm_chunks if c == "glcm" else 1
             if record:
                 e1.record()
                 ev[c].append((e0, e1))
@@ -286,23 +289,31 @@ def run_b200(args):
                 "suite_frac": 625.0 * value / world / 1e9 / peak,
                 "note": "compute-bound fp64/integer kernel: see DESIGN.md section 'roofline'"}
 
-    # ---- e2e through the host-buffer API (N=1 only: maps of one volume returned to one host)
+    # ---- e2e through the host-buffer API: every rank takes its slab (+ halo planes) of the HOST
+    # volume, H2D, discretised-level packing, the five fused kernels, D2H of its slab's 75 maps
     e2e = None
-    if world == 1 and not args.no_e2e:
+    if not args.no_e2e:
         del outs
         torch.cuda.empty_cache()
-        hx = voxel.HostExtractor((Z, Z, Z), CLASSES, dev)
-        msk = np.ones(vol.shape, np.uint8)
-        hx.run(vol, msk, 32, 32)           # warm-up (also faults the pinned pages in)
-        torch.cuda.synchronize()
+        h0, h1 = max(z0 - r, 0), min(z1 + r, Z)
+        hx = voxel.HostExtractor((h1 - h0, Z, Z), CLASSES, dev, z0=z0 - h0, z1=z1 - h0)
+        blk = np.ascontiguousarray(vol[h0:h1])
+        msk = np.ones(blk.shape, np.uint8)
+        hx.run(blk, msk, 32, 32)                             # warm-up (also faults the pinned pages in)
+        barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            hx.run(vol, msk, 32, 32)
+            hx.run(blk, msk, 32, 32)
         torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / args.e2e_steps
-        e2e = {"value": nvox_total / dt, "unit": "voxels/s", "h2d_bytes_per_step": hx.h2d_bytes,
-               "d2h_bytes_per_step": hx.d2h_bytes, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
-               "api": "pyradiomics_b200.voxel.HostExtractor.run (pinned host buffers, D2H overlapped per class)"}
+        dt = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], dtype=torch.float64, device=dev)
+        hb = torch.tensor([hx.h2d_bytes, hx.d2h_bytes], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(hb, op=dist.ReduceOp.SUM)
+        dtv = float(dt.item())
+        e2e = {"value": nvox_total / dtv, "unit": "voxels/s", "h2d_bytes_per_step": int(hb[0].item()),
+               "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": dtv * 1e3, "steps": args.e2e_steps,
+               "api": "pyradiomics_b200.voxel.HostExtractor.run (pinned host buffers per rank, D2H overlapped per class, max over ranks)"}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,

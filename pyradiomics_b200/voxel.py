@@ -104,28 +104,33 @@ class HostExtractor:
     """End-to-end voxel-based extraction with HOST buffers (what a pyradiomics user holds):
     int32 gray levels + mask in, float64 feature maps out, all transfers inside.  Device buffers
     and pinned staging are allocated once and reused; the device->host copy of class k overlaps
-    the kernels of class k+1 on a second stream."""
+    the kernels of class k+1 on a second stream.
 
-    def __init__(self, shape, classes=CLASSES, device=None):
+    `shape` is the (Z,Y,X) block handed to this GPU; `z0:z1` (default everything) selects the
+    planes whose maps are computed and returned -- a multi-GPU caller passes its slab plus halo
+    planes read from the host volume and keeps only the interior (no collective needed)."""
+
+    def __init__(self, shape, classes=CLASSES, device=None, z0=0, z1=None):
         self.shape = tuple(int(s) for s in shape)
         self.classes = tuple(classes)
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.z0, self.z1 = int(z0), int(self.shape[0] if z1 is None else z1)
+        self.out_shape = (self.z1 - self.z0,) + self.shape[1:]
         self.nf = {c: lib().rb_num_features(CLASS_ID[c]) for c in self.classes}
         n = int(np.prod(self.shape))
         self.d_img = torch.empty(self.shape, dtype=torch.int32, device=self.dev)
         self.d_msk = torch.empty(self.shape, dtype=torch.uint8, device=self.dev)
         maxf = max(self.nf.values())
-        self.d_out = [torch.empty((maxf,) + self.shape, dtype=torch.float64, device=self.dev) for _ in range(2)]
+        self.d_out = [torch.empty((maxf,) + self.out_shape, dtype=torch.float64, device=self.dev) for _ in range(2)]
         self.h_img = torch.empty(self.shape, dtype=torch.int32, pin_memory=True)
         self.h_msk = torch.empty(self.shape, dtype=torch.uint8, pin_memory=True)
-        self.h_out = {c: torch.empty((self.nf[c],) + self.shape, dtype=torch.float64, pin_memory=True) for c in self.classes}
+        self.h_out = {c: torch.empty((self.nf[c],) + self.out_shape, dtype=torch.float64, pin_memory=True) for c in self.classes}
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.h2d_bytes = n * 5
-        self.d2h_bytes = sum(self.nf.values()) * n * 8
-        self.launches = 0
+        self.d2h_bytes = sum(self.nf.values()) * int(np.prod(self.out_shape)) * 8
 
-    def run(self, image: np.ndarray, mask: np.ndarray, Ng: int, n_roi_levels: int, **kw):
-        """returns {class: pinned float64 tensor [F,Z,Y,X]} (valid until the next run())."""
+    def run(self, image: np.ndarray, mask: np.ndarray, Ng: int, n_roi_levels: int, alive=None, **kw):
+        """returns {class: pinned float64 tensor [F, z1-z0, Y, X]} (valid until the next run())."""
         self.h_img.numpy()[...] = image
         self.h_msk.numpy()[...] = mask
         cur = torch.cuda.current_stream()
@@ -133,15 +138,16 @@ class HostExtractor:
         self.d_msk.copy_(self.h_msk, non_blocking=True)
         lev, _ = pack_levels(self.d_img, self.d_msk, Ng)
         settings = _lib.make_settings(Ng, n_roi_levels, **kw)
-        self.launches = 1
+        if alive is None and "glcm" in self.classes:
+            from . import distributed as D
+            alive = D.allreduce_alive(glcm_alive_angles(lev, settings), self.dev)   # OR over the slabs' ranks
         done = [None, None]
         for i, c in enumerate(self.classes):
             slot = i & 1
             if done[slot] is not None:
                 cur.wait_event(done[slot])          # the D2H that last used this device buffer
             out = self.d_out[slot][: self.nf[c]]
-            voxel_features(c, lev, settings, out=out, out_z0=0)
-            self.launches += 2 if c == "glcm" else 1
+            voxel_features(c, lev, settings, z0=self.z0, z1=self.z1, out=out, out_z0=self.z0, alive=alive if c == "glcm" else None)
             ev = torch.cuda.Event()
             ev.record(cur)
             with torch.cuda.stream(self.copy_stream):
