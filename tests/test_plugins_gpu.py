@@ -163,3 +163,45 @@ def test_log_size_guards():
     assert list(IO.getLoGImage(I.ArrayImage(np.zeros((3, 8, 8))), None, sigma=[1.0])) == []
     names = [n for _, n, _ in IO.getLoGImage(I.ArrayImage(np.zeros((8, 8, 8), np.float32)), None, sigma=[1.5, -1])]
     assert names == ["log-sigma-1-5-mm-3D"]
+
+
+# ------------------------------------------------------------------------------ pipelines
+def test_filter_pipeline_equals_per_image_plugins():
+    """config-4 shape: original + 8 wavelet bands + LoG sigmas, each binned then run through the
+    fused kernels on the device == doing the same image by image through the plugin classes."""
+    from pyradiomics_b200 import pipeline as PP
+    rng = np.random.default_rng(9)
+    import scipy.ndimage as ndi
+    x = (ndi.gaussian_filter(rng.normal(size=(12, 14, 16)), 1.5) * 400 + 300).astype(np.float32)
+    m = np.ones(x.shape, np.uint8)
+    got = {}
+    info = PP.voxel_suite_with_filters(torch.as_tensor(x).cuda(), torch.as_tensor(m).cuda(), classes=("gldm", "glrlm"),
+                                       sigmas=(1.0,), binWidth=25,
+                                       consume=lambda n, c, t: got.__setitem__((n, c), t.cpu().numpy().copy()))
+    assert len(info) == 1 + 8 + 1
+    names = [n for n, _, _ in info]
+    assert names[0] == "original" and "wavelet-HHH" in names and "wavelet-LLL" in names and names[-1] == "log-sigma-1-0-mm-3D"
+    imgs = {"original": I.ArrayImage(x)}
+    for im, n, _ in IO.getWaveletImage(I.ArrayImage(x), None):
+        imgs[n] = im
+    for im, n, _ in IO.getLoGImage(I.ArrayImage(x), None, sigma=[1.0]):
+        imgs[n] = im
+    for n in names:
+        for c in ("gldm", "glrlm"):
+            ref = FC.FEATURE_CLASSES[c](imgs[n], I.ArrayImage(m), voxelBased=True, binWidth=25).execute()
+            from pyradiomics_b200 import _lib as L
+            for k, f in enumerate(L.feature_names(c)):
+                assert np.allclose(got[(n, c)][k], I.as_array(ref[f]), rtol=1e-9, atol=1e-11, equal_nan=True), (n, c, f)
+
+
+def test_segment_batch_shards_cases(seg):
+    from pyradiomics_b200 import pipeline as PP
+    cases, expect = seg
+    cs = [(cases[c + "_image"], cases[c + "_mask"].astype(np.uint8)) for c in CASES]
+    r0 = PP.segment_batch(cs, classes=("ngtdm",), rank=0, world=2, binWidth=25)
+    r1 = PP.segment_batch(cs, classes=("ngtdm",), rank=1, world=2, binWidth=25)
+    assert sorted(r0) == [0, 2, 4] and sorted(r1) == [1, 3]
+    for k, c in enumerate(CASES):
+        got = (r0 if k % 2 == 0 else r1)[k]["ngtdm"]
+        for f, v in expect["ngtdm"][c]["features"].items():
+            assert abs(got[f] - v) <= 1e-7 * abs(v)
