@@ -7,6 +7,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#define RB_GLCM_BLOCK_SYNC 1   // phase A is called by all threads of a block, uniformly
 #include "glcm_fast.cuh"
 #include "glrlm_fast.cuh"
 #include "host_common.hpp"
@@ -52,18 +53,18 @@ glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ ce
   const int tid = threadIdx.x;
   const long long plane = (long long)P.Y * P.X;
   const long long total = (long long)(z1 - z0) * plane;
-  for (long long t = (long long)blockIdx.x * GF_THREADS + tid; t < total; t += (long long)gridDim.x * GF_THREADS) {
-    const int z = z0 + (int)(t / plane);
-    const int rem = (int)(t % plane);
+  const long long ntiles = (total + GF_THREADS - 1) / GF_THREADS;
+  // block-uniform tile loop: every thread runs phase A (on an all-zero window when its voxel is
+  // not a centre / past the end) so the per-angle barriers inside are reached by the whole block
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long t = tile * GF_THREADS + tid;
+    const bool live = t < total;
+    const int z = z0 + (int)((live ? t : 0) / plane);
+    const int rem = (int)((live ? t : 0) % plane);
     const int y = rem / P.X, x = rem % P.X;
     const long long vi = (long long)z * P.sz + (long long)y * P.sy + x;
     const long long oi = (long long)(z - out_z0) * plane + rem;
-    const bool is_center = centers ? centers[(long long)z * plane + rem] != 0 : lev[vi] != 0;
-    if (!is_center) {
-#pragma unroll
-      for (int k = 0; k < GLCM_NF; k++) out[k * fstride + oi] = P.init_value;
-      continue;
-    }
+    const bool is_center = live && (centers ? centers[(long long)z * plane + rem] != 0 : lev[vi] != 0);
     uint8_t* w = &wbuf[tid];
 #pragma unroll
     for (int dz = -1; dz <= 1; dz++)
@@ -72,13 +73,19 @@ glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ ce
 #pragma unroll
         for (int dx = -1; dx <= 1; dx++) {
           const int zz = z + dz, yy = y + dy, xx = x + dx;
-          const bool in = zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
+          const bool in = is_center && zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
           w[((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)) * GF_THREADS] =
               in ? lev[vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : (uint8_t)0;
         }
     double f[GLCM_NF];
     int n_ok = 0;
     const uint32_t tasks = glcm_fast_voxel_phaseA(w, GF_THREADS, &eqbuf[tid], GF_THREADS, T, P, f, &n_ok);
+    if (!live) continue;
+    if (!is_center) {
+#pragma unroll
+      for (int k = 0; k < GLCM_NF; k++) out[k * fstride + oi] = P.init_value;
+      continue;
+    }
 #pragma unroll
     for (int k = 0; k < GLCM_NF; k++) out[k * fstride + oi] = f[k];
     if (tasks) {
