@@ -37,6 +37,10 @@ bool glrlm_fast_applicable(int cls, int level_bytes, const VoxParams& P);
 int glrlm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P, double* out, long long fstride,
                       int z0, int z1, int out_z0, cudaStream_t st);
 
+bool small_fast_applicable(int cls, int level_bytes, const VoxParams& P);
+int small_fast_launch(int cls, const void* lev, const uint8_t* centers, const VoxParams& P, double* out, long long fstride,
+                      int z0, int z1, int out_z0, cudaStream_t st);
+
 // B200_RADIOMICS_FORCE_GENERIC=1 routes everything through the generic kernels (used by the
 // tests to cross-check the fast paths on the GPU)
 static bool force_generic() {
@@ -148,6 +152,9 @@ int rb_voxel_features_dev(int cls, const void* levels_dev, int level_bytes, cons
   if (!force_generic() && glcm_fast_applicable(cls, level_bytes, P))
     return glcm_fast_launch(levels_dev, centers_dev, P, (double*)out_dev, out_feature_stride, z0, z1, out_z0,
                             (cudaStream_t)stream);
+  if (!force_generic() && small_fast_applicable(cls, level_bytes, P))
+    return small_fast_launch(cls, levels_dev, centers_dev, P, (double*)out_dev, out_feature_stride, z0, z1, out_z0,
+                             (cudaStream_t)stream);
   if (!force_generic() && glrlm_fast_applicable(cls, level_bytes, P))
     return glrlm_fast_launch(levels_dev, centers_dev, P, (double*)out_dev, out_feature_stride, z0, z1, out_z0,
                              (cudaStream_t)stream);

@@ -37,6 +37,9 @@ namespace rb {
 constexpr int GF_NA = 13;
 constexpr int GF_LOGT = 40;       // log2 table covers 0..2*18+1
 constexpr int GF_KT = 256;        // |a-b| tables
+#ifndef RB_LZ_T
+#define RB_LZ_T float
+#endif
 constexpr int GF_BISECT = 27;     // Sturm bisection steps: interval 2/2^27 = 1.5e-8 (tolerance budget 1e-5)
 
 struct GlcmFastTables {
@@ -105,7 +108,8 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const GlcmFastTable
   const uint8_t* pA = T.pA[s];
   const uint8_t* pB = T.pB[s];
   // level nodes (<= 19 for a connected graph with <= 18 edges), R = endpoint multiplicity = row sum
-  double v1[19], q0[19], q1[19], z[19], ew[18];
+  // stored in float (halves the per-thread scratch that has to stay in L1); all arithmetic in double
+  RB_LZ_T v1[19], q0[19], q1[19], z[19], ew[18];
   uint8_t nodelev[19], ei[18], ej[18];
   int n = 0, ne = 0;
   for (int i = 0; i < 19; i++) v1[i] = 0;

@@ -10,6 +10,7 @@
 #define RB_GLCM_BLOCK_SYNC 1   // phase A is called by all threads of a block, uniformly
 #include "glcm_fast.cuh"
 #include "glrlm_fast.cuh"
+#include "small_fast.cuh"
 #include "host_common.hpp"
 
 namespace rb {
@@ -227,7 +228,8 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
     else if (minb == 3) glcm_fast_kernel<3><<<grid, GF_THREADS, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
     else glcm_fast_kernel<2><<<grid, GF_THREADS, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
     RB_LAUNCH_CHECK();
-    glcm_fast_solve_kernel<<<sms * 8, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
+    static const int solve_bps = getenv("B200_GLCM_SOLVE_BPS") ? atoi(getenv("B200_GLCM_SOLVE_BPS")) : 8;
+    glcm_fast_solve_kernel<<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
     RB_LAUNCH_CHECK();
     glcm_fast_finish_kernel<<<sms * 8, 256, 0, st>>>(P, Q->q, Q->count, Q->res, out + (long long)G_MCC * fstride, out_z0);
     RB_LAUNCH_CHECK();
@@ -315,6 +317,98 @@ int glrlm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   long long need = (total + 127) / 128, cap = (long long)sms * 32;
   glrlm_fast_kernel<<<(int)(need < cap ? need : cap), 128, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, z0, z1, out_z0);
+  RB_LAUNCH_CHECK();
+  return RB_OK;
+}
+
+// ------------------------------------------------------------------ GLSZM / GLDM / NGTDM fast paths
+template <int CLS>
+__global__ void __launch_bounds__(128)
+small_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ centers,
+                  const __grid_constant__ VoxParams P, const SmallFastTables* __restrict__ Tg,
+                  double* __restrict__ out, long long fstride, int z0, int z1, int out_z0) {
+  __shared__ SmallFastTables T;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(Tg);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
+    for (int i = threadIdx.x; i < (int)(sizeof(SmallFastTables) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  constexpr int NF = CLS == C_GLSZM ? GLSZM_NF : CLS == C_GLDM ? GLDM_NF : NGTDM_NF;
+  const long long plane = (long long)P.Y * P.X;
+  const long long total = (long long)(z1 - z0) * plane;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int z = z0 + (int)(t / plane);
+    const int rem = (int)(t % plane);
+    const int y = rem / P.X, x = rem % P.X;
+    const long long vi = (long long)z * P.sz + (long long)y * P.sy + x;
+    const long long oi = (long long)(z - out_z0) * plane + rem;
+    const bool is_center = centers ? centers[(long long)z * plane + rem] != 0 : lev[vi] != 0;
+    if (!is_center) {
+#pragma unroll
+      for (int k = 0; k < NF; k++) out[k * fstride + oi] = P.init_value;
+      continue;
+    }
+    int wl[27];
+    {
+      int p = 0;
+#pragma unroll
+      for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+          for (int dx = -1; dx <= 1; dx++, p++) {
+            const int zz = z + dz, yy = y + dy, xx = x + dx;
+            const bool in = zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
+            wl[p] = in ? lev[vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : 0;
+          }
+    }
+    double f[16];
+    if (CLS == C_GLSZM) glszm_fast_voxel(wl, T, f);
+    else if (CLS == C_GLDM) gldm_fast_voxel(wl, P.alpha, T, f);
+    else ngtdm_fast_voxel(wl, T, f);
+#pragma unroll
+    for (int k = 0; k < NF; k++) out[k * fstride + oi] = f[k];
+  }
+}
+
+static const SmallFastTables* small_fast_tables_dev() {
+  static std::mutex mu;
+  static std::map<int, SmallFastTables*> cache;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(dev);
+  if (it != cache.end()) return it->second;
+  SmallFastTables* h = new SmallFastTables;
+  small_fast_build_tables(*h);
+  SmallFastTables* d = nullptr;
+  if (cudaMalloc(&d, sizeof *h) != cudaSuccess || cudaMemcpy(d, h, sizeof *h, cudaMemcpyHostToDevice) != cudaSuccess) { delete h; return nullptr; }
+  delete h;
+  cache[dev] = d;
+  return d;
+}
+
+bool small_fast_applicable(int cls, int level_bytes, const VoxParams& P) {
+  return (cls == C_GLSZM || cls == C_GLDM || cls == C_NGTDM) && level_bytes == 1 && P.rz == 1 && P.ry == 1 && P.rx == 1 &&
+         P.na == 26 && P.Ng <= 255;
+}
+
+int small_fast_launch(int cls, const void* lev, const uint8_t* centers, const VoxParams& P, double* out, long long fstride,
+                      int z0, int z1, int out_z0, cudaStream_t st) {
+  const SmallFastTables* T = small_fast_tables_dev();
+  if (!T) return fail(RB_ERR_CUDA, "could not build the table block on the device");
+  const long long total = (long long)(z1 - z0) * P.Y * P.X;
+  if (total <= 0) return RB_OK;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long need = (total + 127) / 128, cap = (long long)sms * 32;
+  const int grid = (int)(need < cap ? need : cap);
+  const uint8_t* l8 = (const uint8_t*)lev;
+  if (cls == C_GLSZM) small_fast_kernel<C_GLSZM><<<grid, 128, 0, st>>>(l8, centers, P, T, out, fstride, z0, z1, out_z0);
+  else if (cls == C_GLDM) small_fast_kernel<C_GLDM><<<grid, 128, 0, st>>>(l8, centers, P, T, out, fstride, z0, z1, out_z0);
+  else small_fast_kernel<C_NGTDM><<<grid, 128, 0, st>>>(l8, centers, P, T, out, fstride, z0, z1, out_z0);
   RB_LAUNCH_CHECK();
   return RB_OK;
 }

@@ -100,3 +100,29 @@ extern "C" int emul_glrlm_fast(const uint16_t* lev, int Z, int Y, int X, const V
   delete T;
   return 0;
 }
+
+#include "../../pyradiomics_b200/csrc/small_fast.cuh"
+// GLSZM / GLDM / NGTDM fast paths (r=1, 26-neighbourhood, 8-bit levels) on the host
+extern "C" int emul_small_fast(int cls, const uint16_t* lev, int Z, int Y, int X, const VoxSettings* s, double* out) {
+  VoxParams P;
+  int rc = fill_vox_params(cls, Z, Y, X, *s, P);
+  if (rc) return rc;
+  if (P.na != 26 || P.rz != 1 || P.ry != 1 || P.rx != 1 || s->Ng > 255) return -5;
+  SmallFastTables* T = new SmallFastTables;
+  small_fast_build_tables(*T);
+  const int nf = kNumFeatures[cls];
+  const long long nvox = (long long)Z * Y * X;
+  for (int z = 0; z < Z; z++) for (int y = 0; y < Y; y++) for (int x = 0; x < X; x++) {
+    long long i = ((long long)z * Y + y) * X + x;
+    if (!lev[i]) { for (int k = 0; k < nf; k++) out[k * nvox + i] = P.init_value; continue; }
+    uint16_t w16[27]; int wl[27]; double f[16];
+    load_window<uint16_t>(lev, P, z, y, x, w16);
+    for (int k = 0; k < 27; k++) wl[k] = w16[k];
+    if (cls == C_GLSZM) glszm_fast_voxel(wl, *T, f);
+    else if (cls == C_GLDM) gldm_fast_voxel(wl, P.alpha, *T, f);
+    else ngtdm_fast_voxel(wl, *T, f);
+    for (int k = 0; k < nf; k++) out[k * nvox + i] = f[k];
+  }
+  delete T;
+  return 0;
+}

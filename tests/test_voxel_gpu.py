@@ -83,7 +83,8 @@ def test_slab_and_reflection_properties_at_scale(cname):
     flipped = voxel.voxel_features(cname, lev.flip(2).contiguous(), s).flip(3)
     a, b = whole.cpu().numpy(), flipped.cpu().numpy()
     assert np.isfinite(a).all()
-    assert np.allclose(a, b, rtol=1e-9, atol=1e-12)
+    # MCC eigen-tasks keep their Lanczos vectors in float32: reflection-invariant to ~1e-7 only
+    assert np.allclose(a, b, rtol=2e-6 if cname == "glcm" else 1e-9, atol=1e-12)
 
 
 def test_tensor_api_matches_host_api():
@@ -122,5 +123,19 @@ def test_glrlm_fast_path_equals_generic_kernel(kind, monkeypatch):
     fast = voxel.voxel_features("glrlm", lev, s).cpu().numpy()
     monkeypatch.setenv("B200_RADIOMICS_FORCE_GENERIC", "1")
     gen = voxel.voxel_features("glrlm", lev, s).cpu().numpy()
+    monkeypatch.delenv("B200_RADIOMICS_FORCE_GENERIC")
+    assert np.allclose(fast, gen, rtol=1e-10, atol=1e-12, equal_nan=True)
+
+
+@pytest.mark.parametrize("cname", ["glszm", "gldm", "ngtdm"])
+@pytest.mark.parametrize("kind,alpha", [("uniform", 0), ("smooth", 0), ("smooth", 2)])
+def test_small_class_fast_paths_equal_generic_kernel(cname, kind, alpha, monkeypatch):
+    lev = torch.as_tensor(_random_volume(kind, (36, 40, 44), 4).astype(np.uint8)).cuda()
+    lev[5:9, 3:30, 7] = 0
+    lev[20, :, :] = 0
+    s = _lib.make_settings(32, 32, gldm_a=alpha)
+    fast = voxel.voxel_features(cname, lev, s).cpu().numpy()
+    monkeypatch.setenv("B200_RADIOMICS_FORCE_GENERIC", "1")
+    gen = voxel.voxel_features(cname, lev, s).cpu().numpy()
     monkeypatch.delenv("B200_RADIOMICS_FORCE_GENERIC")
     assert np.allclose(fast, gen, rtol=1e-10, atol=1e-12, equal_nan=True)
