@@ -186,22 +186,22 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const GlcmFastTable
     }
     // largest eigenvalue of the deflated tridiagonal, then the most negative one only if some
     // eigenvalue lies below -|hi| (one extra Sturm evaluation decides)
-    const double hi = tridiag_kth_eigenvalue(d, e, m, m - 1, -1.0 - 1e-6, 1.0 + 1e-6, GF_BISECT);
+    // (the Lanczos betas are > 1e-10, so T is unreduced: simple eigenvalues, Laguerre is safe)
+    const double hi = tridiag_extreme_eigenvalue(d, e, m, true);
     double lo = 0;
     {
       const double x = -fabs(hi) - 1e-7;
-      // count(x) > 0  <=>  the smallest eigenvalue is <= x  <=>  bisection of k=0 on [-1-d, x] is needed
+      // Sturm count at x: is any eigenvalue <= -|hi| ?  only then the most negative one matters
       double pm2 = 1.0, pm1 = d[0] - x; int cnt = pm1 <= 0;
       for (int i = 1; i < m && !cnt; i++) {
         const double e2 = e[i] * e[i];
-        if (e2 == 0) { pm2 = 1.0; pm1 = d[i] - x; cnt += pm1 <= 0; continue; }
         const double p = (d[i] - x) * pm1 - e2 * pm2;
         const bool neg_prev = pm1 < 0 || (pm1 == 0 && pm2 > 0);
         const bool neg_cur = p < 0 || (p == 0 && !neg_prev);
         cnt += neg_cur != neg_prev;
         pm2 = pm1; pm1 = p;
       }
-      if (cnt) lo = tridiag_kth_eigenvalue(d, e, m, 0, -1.0 - 1e-6, x, GF_BISECT);
+      if (cnt) lo = tridiag_extreme_eigenvalue(d, e, m, false);
     }
     best = fmax(best, fmax(fabs(hi), fabs(lo)));
     if (m == n - 1) break;

@@ -196,6 +196,41 @@ static RB_HDN double tridiag_kth_eigenvalue(const double* d, const double* e, in
   return 0.5 * (lo + hi);
 }
 
+// Extreme eigenvalue (largest if `top`, else smallest) of an UNREDUCED symmetric tridiagonal (d, e)
+// by Laguerre's iteration on the characteristic polynomial p(x) = det(T - x I), started outside the
+// spectrum at a Gershgorin bound: for a polynomial with only real roots it converges monotonically
+// and cubically to the nearest (= extreme) root.  p, p', p'' come from the three-term recurrence.
+// Falls back to Sturm bisection if it has not converged after 40 steps.
+static RB_HDN double tridiag_extreme_eigenvalue(const double* d, const double* e, int n, bool top) {
+  double lo = d[0], hi = d[0];
+  for (int i = 0; i < n; i++) {
+    const double r = (i > 0 ? fabs(e[i]) : 0.0) + (i + 1 < n ? fabs(e[i + 1]) : 0.0);
+    lo = fmin(lo, d[i] - r); hi = fmax(hi, d[i] + r);
+  }
+  if (n == 1) return d[0];
+  double x = top ? hi + 1e-9 : lo - 1e-9;
+  for (int it = 0; it < 40; it++) {
+    double p0 = 1.0, p1 = d[0] - x, q0 = 0.0, q1 = -1.0, r0 = 0.0, r1 = 0.0;   // p, p', p''
+    for (int i = 1; i < n; i++) {
+      const double a = d[i] - x, b = e[i] * e[i];
+      const double p2 = a * p1 - b * p0;
+      const double q2 = a * q1 - p1 - b * q0;
+      const double r2 = a * r1 - 2.0 * q1 - b * r0;
+      p0 = p1; p1 = p2; q0 = q1; q1 = q2; r0 = r1; r1 = r2;
+    }
+    if (p1 == 0) return x;
+    const double G = q1 / p1, H = G * G - r1 / p1;
+    const double disc = (double)(n - 1) * ((double)n * H - G * G);
+    const double sq = sqrt(disc > 0 ? disc : 0.0);
+    const double den = fabs(G + sq) > fabs(G - sq) ? G + sq : G - sq;
+    if (den == 0 || den != den) break;
+    const double step = (double)n / den;
+    x -= step;
+    if (fabs(step) < 1e-11) return x;
+  }
+  return tridiag_kth_eigenvalue(d, e, n, top ? n - 1 : 0, lo - 1e-9, hi + 1e-9, 40);
+}
+
 // Second-largest eigenvalue of a symmetric positive semi-definite matrix with spectrum in [0, 1+]
 // (the generic MCC path: A = M M^T).  n >= 2.
 static RB_HDN double sym_psd_second_largest(double* A, int n, int ld, double* d, double* e) {

@@ -36,29 +36,29 @@ struct GlcmTask {
   float unused;
 };
 
-template <int MINB>
-__global__ void __launch_bounds__(GF_THREADS, MINB)
+template <int MINB, int NT>
+__global__ void __launch_bounds__(NT, MINB)
 glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ centers,
                  const __grid_constant__ VoxParams P, const GlcmFastTables* __restrict__ Tg,
                  double* __restrict__ out, long long fstride, int z0, int z1, int out_z0,
                  GlcmTask* __restrict__ queue, unsigned* __restrict__ qcount) {
   __shared__ GlcmFastTables T;
-  __shared__ uint8_t wbuf[27 * GF_THREADS];
-  __shared__ uint32_t eqbuf[27 * GF_THREADS];
+  __shared__ uint8_t wbuf[27 * NT];
+  __shared__ uint32_t eqbuf[27 * NT];
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(Tg);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
-    for (int i = threadIdx.x; i < (int)(sizeof(GlcmFastTables) / 4); i += GF_THREADS) dst[i] = src[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(GlcmFastTables) / 4); i += NT) dst[i] = src[i];
   }
   __syncthreads();
   const int tid = threadIdx.x;
   const long long plane = (long long)P.Y * P.X;
   const long long total = (long long)(z1 - z0) * plane;
-  const long long ntiles = (total + GF_THREADS - 1) / GF_THREADS;
+  const long long ntiles = (total + NT - 1) / NT;
   // block-uniform tile loop: every thread runs phase A (on an all-zero window when its voxel is
   // not a centre / past the end) so the per-angle barriers inside are reached by the whole block
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long t = tile * GF_THREADS + tid;
+    const long long t = tile * NT + tid;
     const bool live = t < total;
     const int z = z0 + (int)((live ? t : 0) / plane);
     const int rem = (int)((live ? t : 0) % plane);
@@ -75,12 +75,12 @@ glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ ce
         for (int dx = -1; dx <= 1; dx++) {
           const int zz = z + dz, yy = y + dy, xx = x + dx;
           const bool in = is_center && zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
-          w[((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)) * GF_THREADS] =
+          w[((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)) * NT] =
               in ? lev[vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : (uint8_t)0;
         }
     double f[GLCM_NF];
     int n_ok = 0;
-    const uint32_t tasks = glcm_fast_voxel_phaseA(w, GF_THREADS, &eqbuf[tid], GF_THREADS, T, P, f, &n_ok);
+    const uint32_t tasks = glcm_fast_voxel_phaseA(w, NT, &eqbuf[tid], NT, T, P, f, &n_ok);
     if (!live) continue;
     if (!is_center) {
 #pragma unroll
@@ -223,10 +223,13 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
     RB_CUDA(cudaMemsetAsync(Q->count, 0, sizeof(unsigned), st));
     long long need = (total + GF_THREADS - 1) / GF_THREADS, cap = (long long)sms * 16;
     const int grid = (int)(need < cap ? need : cap);
-    static const int minb = getenv("B200_GLCM_MINB") ? atoi(getenv("B200_GLCM_MINB")) : 2;
-    if (minb >= 4) glcm_fast_kernel<4><<<grid, GF_THREADS, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
-    else if (minb == 3) glcm_fast_kernel<3><<<grid, GF_THREADS, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
-    else glcm_fast_kernel<2><<<grid, GF_THREADS, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
+    static const int nt = getenv("B200_GLCM_NT") ? atoi(getenv("B200_GLCM_NT")) : 128;
+    if (nt == 256) {
+      long long need2 = (total + 255) / 256, cap2 = (long long)sms * 8;
+      glcm_fast_kernel<1, 256><<<(int)(need2 < cap2 ? need2 : cap2), 256, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
+    } else {
+      glcm_fast_kernel<2, 128><<<grid, 128, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
+    }
     RB_LAUNCH_CHECK();
     static const int solve_bps = getenv("B200_GLCM_SOLVE_BPS") ? atoi(getenv("B200_GLCM_SOLVE_BPS")) : 8;
     glcm_fast_solve_kernel<<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
