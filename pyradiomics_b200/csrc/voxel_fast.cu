@@ -32,7 +32,7 @@ struct GlcmTask {
   uint8_t slot;        // angle slot to solve
   uint8_t n_ok;        // number of non-empty angles of the voxel (the nanmean denominator)
   uint8_t count;       // > 0 on the first task of a voxel: how many consecutive entries belong to it
-  uint8_t pad;
+  uint8_t cls;         // size class of the task (0..3), used to group similar tasks in a warp
   float unused;
 };
 
@@ -80,7 +80,8 @@ glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ ce
         }
     double f[GLCM_NF];
     int n_ok = 0;
-    const uint32_t tasks = glcm_fast_voxel_phaseA(w, NT, &eqbuf[tid], NT, T, P, f, &n_ok);
+    unsigned long long tcls = 0;
+    const uint32_t tasks = glcm_fast_voxel_phaseA(w, NT, &eqbuf[tid], NT, T, P, f, &n_ok, &tcls);
     if (!live) continue;
     if (!is_center) {
 #pragma unroll
@@ -96,7 +97,7 @@ glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ ce
       for (uint32_t m = tasks; m; m &= m - 1, q++) {
         GlcmTask e;
         e.vi = vi; e.slot = (uint8_t)(__ffs((int)m) - 1); e.n_ok = (uint8_t)n_ok; e.count = first ? (uint8_t)k : 0;
-        e.pad = 0; e.unused = 0.f;
+        e.cls = (uint8_t)(tcls >> (3 * e.slot) & 7u); e.unused = 0.f;
         queue[q] = e;
         first = false;
       }
@@ -116,22 +117,55 @@ glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ 
   }
   __syncthreads();
   const unsigned n = *qcount;
-  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const GlcmTask e = queue[k];
-    const int z = (int)(e.vi / P.sz), rem = (int)(e.vi % P.sz), y = rem / (int)P.sy, x = rem % (int)P.sy;
-    uint8_t w[27];
-    int p = 0;
+  // Tiles of 8 x 128 consecutive tasks are counting-sorted by size class in shared memory, so the
+  // lanes of a warp run Lanczos recurrences of similar length (ncu: 14 of 32 lanes active before).
+  constexpr int TILE = 1024;
+  __shared__ uint16_t order[TILE];
+  __shared__ int bucket[8];
+  const unsigned ntiles = (n + TILE - 1) / TILE;
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const unsigned base = tile * TILE;
+    if (threadIdx.x < 8) bucket[threadIdx.x] = 0;
+    __syncthreads();
+    uint8_t mycls[TILE / 128];
 #pragma unroll
-    for (int dz = -1; dz <= 1; dz++)
+    for (int j = 0; j < TILE / 128; j++) {
+      const unsigned k = base + j * 128 + threadIdx.x;
+      mycls[j] = k < n ? queue[k].cls : 8;
+      if (mycls[j] < 8) atomicAdd(&bucket[mycls[j]], 1);
+    }
+    __syncthreads();
+    int start[8];
+    start[0] = 0;
 #pragma unroll
-      for (int dy = -1; dy <= 1; dy++)
+    for (int c = 1; c < 8; c++) start[c] = start[c - 1] + bucket[c - 1];
+    const int ntile = start[7] + bucket[7];
+    __syncthreads();
+    if (threadIdx.x < 8) bucket[threadIdx.x] = start[threadIdx.x];
+    __syncthreads();
 #pragma unroll
-        for (int dx = -1; dx <= 1; dx++, p++) {
-          const int zz = z + dz, yy = y + dy, xx = x + dx;
-          const bool in = zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
-          w[p] = in ? lev[e.vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : (uint8_t)0;
-        }
-    res[k] = glcm_fast_solve_task(w, 1, T, e.slot);
+    for (int j = 0; j < TILE / 128; j++)
+      if (mycls[j] < 8) order[atomicAdd(&bucket[mycls[j]], 1)] = (uint16_t)(j * 128 + threadIdx.x);
+    __syncthreads();
+    for (int i = threadIdx.x; i < ntile; i += 128) {
+      const unsigned k = base + order[i];
+      const GlcmTask e = queue[k];
+      const int z = (int)(e.vi / P.sz), rem = (int)(e.vi % P.sz), y = rem / (int)P.sy, x = rem % (int)P.sy;
+      uint8_t w[27];
+      int p = 0;
+#pragma unroll
+      for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+          for (int dx = -1; dx <= 1; dx++, p++) {
+            const int zz = z + dz, yy = y + dy, xx = x + dx;
+            const bool in = zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
+            w[p] = in ? lev[e.vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : (uint8_t)0;
+          }
+      res[k] = glcm_fast_solve_task(w, 1, T, e.slot);
+    }
+    __syncthreads();
   }
 }
 
@@ -223,7 +257,7 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
     RB_CUDA(cudaMemsetAsync(Q->count, 0, sizeof(unsigned), st));
     long long need = (total + GF_THREADS - 1) / GF_THREADS, cap = (long long)sms * 16;
     const int grid = (int)(need < cap ? need : cap);
-    static const int nt = getenv("B200_GLCM_NT") ? atoi(getenv("B200_GLCM_NT")) : 128;
+    static const int nt = getenv("B200_GLCM_NT") ? atoi(getenv("B200_GLCM_NT")) : 256;
     if (nt == 256) {
       long long need2 = (total + 255) / 256, cap2 = (long long)sms * 8;
       glcm_fast_kernel<1, 256><<<(int)(need2 < cap2 ? need2 : cap2), 256, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
