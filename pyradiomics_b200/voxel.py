@@ -103,25 +103,29 @@ def extract_maps(image, mask, classes=CLASSES, **kw):
 class HostExtractor:
     """End-to-end voxel-based extraction with HOST buffers (what a pyradiomics user holds):
     int32 gray levels + mask in, float64 feature maps out, all transfers inside.  Device buffers
-    and pinned staging are allocated once and reused; the device->host copy of class k overlaps
-    the kernels of class k+1 on a second stream.
+    and pinned staging are allocated once and reused.  The 80 GB of result maps is what bounds
+    this path (PCIe), so the device->host stream is kept busy from the first milliseconds: classes
+    run in order of (bytes out / compute time), every class is cut into z-chunks, and a chunk's
+    maps are copied on a second stream while the next chunk / class computes.
 
     `shape` is the (Z,Y,X) block handed to this GPU; `z0:z1` (default everything) selects the
     planes whose maps are computed and returned -- a multi-GPU caller passes its slab plus halo
     planes read from the host volume and keeps only the interior (no collective needed)."""
 
-    def __init__(self, shape, classes=CLASSES, device=None, z0=0, z1=None):
+    ORDER = ("gldm", "glszm", "glrlm", "ngtdm", "glcm")      # cheap-and-wide first, GLCM last
+
+    def __init__(self, shape, classes=CLASSES, device=None, z0=0, z1=None, zchunk=64):
         self.shape = tuple(int(s) for s in shape)
-        self.classes = tuple(classes)
+        self.classes = tuple(c for c in self.ORDER if c in classes)
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         self.z0, self.z1 = int(z0), int(self.shape[0] if z1 is None else z1)
+        self.zchunk = int(zchunk)
         self.out_shape = (self.z1 - self.z0,) + self.shape[1:]
         self.nf = {c: lib().rb_num_features(CLASS_ID[c]) for c in self.classes}
         n = int(np.prod(self.shape))
         self.d_img = torch.empty(self.shape, dtype=torch.int32, device=self.dev)
         self.d_msk = torch.empty(self.shape, dtype=torch.uint8, device=self.dev)
-        maxf = max(self.nf.values())
-        self.d_out = [torch.empty((maxf,) + self.out_shape, dtype=torch.float64, device=self.dev) for _ in range(2)]
+        self.d_out = {c: torch.empty((self.nf[c],) + self.out_shape, dtype=torch.float64, device=self.dev) for c in self.classes}
         self.h_img = torch.empty(self.shape, dtype=torch.int32, pin_memory=True)
         self.h_msk = torch.empty(self.shape, dtype=torch.uint8, pin_memory=True)
         self.h_out = {c: torch.empty((self.nf[c],) + self.out_shape, dtype=torch.float64, pin_memory=True) for c in self.classes}
@@ -134,6 +138,7 @@ class HostExtractor:
         self.h_img.numpy()[...] = image
         self.h_msk.numpy()[...] = mask
         cur = torch.cuda.current_stream()
+        self.copy_stream.wait_stream(cur)
         self.d_img.copy_(self.h_img, non_blocking=True)
         self.d_msk.copy_(self.h_msk, non_blocking=True)
         lev, _ = pack_levels(self.d_img, self.d_msk, Ng)
@@ -141,20 +146,18 @@ class HostExtractor:
         if alive is None and "glcm" in self.classes:
             from . import distributed as D
             alive = D.allreduce_alive(glcm_alive_angles(lev, settings), self.dev)   # OR over the slabs' ranks
-        done = [None, None]
-        for i, c in enumerate(self.classes):
-            slot = i & 1
-            if done[slot] is not None:
-                cur.wait_event(done[slot])          # the D2H that last used this device buffer
-            out = self.d_out[slot][: self.nf[c]]
-            voxel_features(c, lev, settings, z0=self.z0, z1=self.z1, out=out, out_z0=self.z0, alive=alive if c == "glcm" else None)
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            with torch.cuda.stream(self.copy_stream):
-                self.copy_stream.wait_event(ev)
-                self.h_out[c].copy_(out, non_blocking=True)
-                done[slot] = torch.cuda.Event()
-                done[slot].record(self.copy_stream)
+        for c in self.classes:
+            out = self.d_out[c]
+            for za in range(self.z0, self.z1, self.zchunk):
+                zb = min(za + self.zchunk, self.z1)
+                voxel_features(c, lev, settings, z0=za, z1=zb, out=out, out_z0=self.z0, alive=alive if c == "glcm" else None)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                with torch.cuda.stream(self.copy_stream):
+                    self.copy_stream.wait_event(ev)
+                    a, b = za - self.z0, zb - self.z0
+                    for f in range(self.nf[c]):          # contiguous [zb-za, Y, X] slabs of each map
+                        self.h_out[c][f, a:b].copy_(out[f, a:b], non_blocking=True)
         self.copy_stream.synchronize()
         cur.synchronize()
         return self.h_out

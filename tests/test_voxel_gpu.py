@@ -139,3 +139,21 @@ def test_small_class_fast_paths_equal_generic_kernel(cname, kind, alpha, monkeyp
     gen = voxel.voxel_features(cname, lev, s).cpu().numpy()
     monkeypatch.delenv("B200_RADIOMICS_FORCE_GENERIC")
     assert np.allclose(fast, gen, rtol=1e-10, atol=1e-12, equal_nan=True)
+
+
+def test_host_extractor_chunks_and_halo_block():
+    """the e2e host-buffer path: z-chunked kernels + per-map D2H copies == the device API; the
+    z0:z1 interior of a block with halo planes == the same planes of the whole volume"""
+    lev = _random_volume("smooth", (11, 10, 9), 6)
+    msk = np.ones(lev.shape, np.uint8)
+    dev = torch.as_tensor(lev.astype(np.uint8)).cuda()
+    s = _lib.make_settings(32, 32)
+    hx = voxel.HostExtractor(lev.shape, zchunk=3)
+    res = hx.run(lev, msk, 32, 32)
+    for c in _lib.CLASSES:
+        assert np.array_equal(res[c].numpy(), voxel.voxel_features(c, dev, s).cpu().numpy()), c
+    hx2 = voxel.HostExtractor((7, 10, 9), classes=("glrlm", "ngtdm"), z0=1, z1=6, zchunk=2)
+    full_alive = None
+    res2 = hx2.run(lev[3:10], msk[3:10], 32, 32)
+    for c in ("glrlm", "ngtdm"):
+        assert np.array_equal(res2[c].numpy(), voxel.voxel_features(c, dev, s, z0=4, z1=9).cpu().numpy()), c
