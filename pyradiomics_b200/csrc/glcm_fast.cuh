@@ -227,7 +227,7 @@ struct GlcmAcc {
 
 // one angle (slot s) of one voxel.  w: the 27 window levels (stride ws), eq: equality masks.
 template <int NP>
-RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es, uint32_t repmask,
+RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
                            const GlcmFastTables& T, int s, const VoxParams& P, GlcmAcc& acc) {
   const uint8_t* pA = T.pA[s];
   const uint8_t* pB = T.pB[s];
@@ -236,6 +236,7 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
   int key1[NP], key2[NP];
   uint32_t valid = 0, EA = 0, EB = 0;
   int n = 0, Ssum = 0, Sab = 0, Sq = 0, Skd = 0;
+  bool selfloop = false;
 #pragma unroll
   for (int t = 0; t < NP; t++) {
     const int a = w[pA[t] * ws], b = w[pB[t] * ws];
@@ -246,6 +247,7 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
     if (ok) {
       valid |= 1u << t; EA |= 1u << pA[t]; EB |= 1u << pB[t];
       n++; Ssum += ks; Sab += a * b; Sq += a * a + b * b; Skd += kd;
+      selfloop |= kd == 0;
     }
   }
   const int orig = T.orig[s];
@@ -253,99 +255,30 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
     if (P.alive[orig >> 5] >> (orig & 31) & 1u) acc.ja_nan = true;
     return;
   }
-  if (NP == 18) { RB_SORTNET_18(key1); RB_SORTNET_18(key2); }
-  else if (NP == 12) { RB_SORTNET_12(key1); RB_SORTNET_12(key2); }
-  else { RB_SORTNET_8(key1); RB_SORTNET_8(key2); }
-  // S = 2n entries' worth of counts.  Every moment below is an exact integer numerator over a
-  // power of S (no cancellation between rounded quantities).
-  const int S2 = 2 * n;
-  const double S = (double)S2, invS = 1.0 / S, invS2 = invS * invS;
-  const double ux = Ssum * invS;
-  const double ac = 2.0 * Sab * invS;
-  const double contrast = 2.0 * (double)(Sq - 2 * Sab) * invS;
-  const int vnum = S2 * Sq - Ssum * Ssum;                       // S^2 * var_x  (>= 0, exact)
-  const double sxx = vnum * invS2;
-  const double sxy = (double)(2 * Sab * S2 - Ssum * Ssum) * invS2;
-  const double ct = (double)(2 * (Sq + 2 * Sab) * S2 - 4 * Ssum * Ssum) * invS2;
-  const double da = 2.0 * Skd * invS;
-  const double dvar = (double)(2 * (Sq - 2 * Sab) * S2 - 4 * Skd * Skd) * invS2;
-  // scan the sorted keys: runs of equal key1 = merged matrix entries (length nn), runs of equal
-  // a+b = p_{x+y} bins, runs of equal key2 = p_{x-y} bins
-  double cs = 0, cp = 0, idm = 0, idmn = 0, id = 0, idn = 0, inv = 0, lgE = 0, lgD = 0, lgS = 0;
-  int E2 = 0, cmax = 0, runK = 0, runS = 0, runD = 0;
+  // ---- level classes of the pair ends: marginal entropy and the level graph of this angle.
+  // R(level) = number of matrix entries in its row = popcount(class & EA) + popcount(class & EB);
+  // sum_levels R log2 R = sum over the 2n pair ends of log2 R(their level).
+  double rl = 0;
+  uint32_t reps = 0, all = 0, comp = 0;
+  uint32_t em[NP];
 #pragma unroll
-  for (int i = 0; i < NP; i++) {
-    if (i < n) {
-      const int k1 = key1[i], ks = k1 >> 8, kd = k1 & 255;
-      const double dn = (double)(ks * n - Ssum), d2 = dn * dn;   // (i+j-ux-uy) * n, an integer
-      cs += d2 * dn; cp += d2 * d2;
-      idm += T.idm[kd]; idmn += T.idmn[kd]; id += T.id[kd]; idn += T.idn[kd]; inv += T.inv[kd];
-      const int nx1 = (i + 1 < NP) ? key1[i + 1 < NP ? i + 1 : i] : -1;
-      const int nx2 = (i + 1 < NP) ? key2[i + 1 < NP ? i + 1 : i] : -1;
-      const bool last = (i + 1 == n);
-      runK++; runS++; runD++;
-      if (last || nx1 != k1) {                 // end of a merged-entry run
-        const int c = kd ? runK : 2 * runK;    // count of the matrix entry (both orders when i != j)
-        E2 += kd ? 2 * runK * runK : 4 * runK * runK;
-        if (c > cmax) cmax = c;
-        lgE += runK * T.log2t[c];
-        runK = 0;
-      }
-      if (last || (nx1 >> 8) != ks) { lgS += runS * T.log2t[2 * runS]; runS = 0; }
-      if (last || nx2 != key2[i]) { lgD += runD * T.log2t[2 * runD]; runD = 0; }
+  for (int t = 0; t < NP; t++) {
+    em[t] = 0;
+    if (valid >> t & 1u) {
+      const uint32_t ea = eq[pA[t] * es], eb = eq[pB[t] * es];
+      rl += T.log2t[RB_POPC(ea & EA) + RB_POPC(ea & EB)] + T.log2t[RB_POPC(eb & EA) + RB_POPC(eb & EB)];
+      reps |= (ea & (0u - ea)) | (eb & (0u - eb));          // lowest position of each class
+      em[t] = ea | eb;
+      all |= em[t];
+      if (!comp) comp = em[t];
     }
   }
-  const double invn = 1.0 / n, invn2 = invn * invn;
-  const double lS = T.log2t[2 * n];
-  const double hxy = -2.0 * invS * (lgE - n * lS);
-  const double dent = -2.0 * invS * (lgD - n * lS);
-  const double sent = -2.0 * invS * (lgS - n * lS);
-  // marginal entropy HX0 = -sum_levels (R/S) log2(R/S),  R = endpoint multiplicity of the level
-  double rl = 0; int nlev = 0;
-  const uint32_t used = EA | EB;
-#pragma unroll
-  for (int v = 0; v < 27; v++) {
-    if (repmask >> v & 1u) {
-      const uint32_t e = eq[v * es];
-      if (e & used) {
-        const int R = RB_POPC(e & EA) + RB_POPC(e & EB);
-        rl += R * T.log2t[R]; nlev++;
-      }
-    }
-  }
-  const double hx0 = nlev > 1 ? lS - rl * invS : 0.0;   // one level: exactly 0 (avoids 0/rounding in Imc1)
-  // HX = HY = hx0 and HXY1 = HXY2 = 2*hx0 (sum_ij p log2(px py) = sum_i px log2 px + sum_j py log2 py);
-  // the reference's "+eps" inside each log2 shifts these by < 1e-13 and is dropped consistently.
-  const double hx = hx0, hxy2 = 2.0 * hx0, hxy1 = hxy2;
-  double f[GLCM_NF];
-  f[G_Autocorrelation] = ac; f[G_JointAverage] = ux;
-  f[G_ClusterProminence] = cp * invn2 * invn2 * invn; f[G_ClusterShade] = cs * invn2 * invn2; f[G_ClusterTendency] = ct;
-  f[G_Contrast] = contrast;
-  f[G_Correlation] = (vnum == 0) ? 1.0 : sxy / (sxx + EPS);
-  f[G_DifferenceAverage] = da; f[G_DifferenceEntropy] = dent; f[G_DifferenceVariance] = dvar;
-  f[G_JointEnergy] = E2 * invS2; f[G_JointEntropy] = hxy;
-  f[G_Imc1] = (hx != 0) ? (hxy - hxy1) / hx : 0.0;
-  // exactly independent margins give HXY2 == HXY in the reference (value 0); here the two are
-  // built from different table sums, so "equal" means equal to rounding
-  const double dxy = hxy2 - hxy;
-  f[G_Imc2] = (fabs(dxy) < 1e-12) ? 0.0 : sqrt(1.0 - exp(-2.0 * dxy));
-  f[G_Idm] = 2.0 * idm * invS; f[G_Idmn] = 2.0 * idmn * invS; f[G_Id] = 2.0 * id * invS; f[G_Idn] = 2.0 * idn * invS;
-  f[G_InverseVariance] = 2.0 * inv * invS;
-  f[G_MaximumProbability] = cmax * invS; f[G_SumAverage] = 2.0 * ux; f[G_SumEntropy] = sent; f[G_SumSquares] = sxx;
-  // ---- MCC
+  const int nlev = RB_POPC(reps);
+  // ---- MCC classification (glcm.py:679-707, see file header): components / bipartite / eigen-task
   double mcc;
   if (P.n_roi_levels < 2) mcc = 1.0;
   else if (nlev < 2) mcc = 0.0;
   else {
-    // connectivity of the level graph by mask propagation over the edges
-    uint32_t em[NP];
-    uint32_t comp = 0, all = 0;
-#pragma unroll
-    for (int t = 0; t < NP; t++) {
-      em[t] = (valid >> t & 1u) ? (eq[pA[t] * es] | eq[pB[t] * es]) : 0u;
-      all |= em[t];
-      if (!comp) comp = em[t];
-    }
     for (int sweep = 0; sweep < NP; sweep++) {
       const uint32_t before = comp;
 #pragma unroll
@@ -356,7 +289,7 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
     else {
       // connected.  A bipartite level graph (no level paired with itself, no odd cycle) has the
       // eigenvalue -1 next to +1 -> second largest |eigenvalue| = 1 without a solve.
-      bool bip = key2[0] != 0;               // smallest |a-b| == 0  <=>  some pair (a,a): self-loop
+      bool bip = !selfloop;
       if (bip) {
         uint32_t A = 0, B = 0;
 #pragma unroll
@@ -383,6 +316,76 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
       }
     }
   }
+  if (NP == 18) { RB_SORTNET_18(key1); RB_SORTNET_18(key2); }
+  else if (NP == 12) { RB_SORTNET_12(key1); RB_SORTNET_12(key2); }
+  else { RB_SORTNET_8(key1); RB_SORTNET_8(key2); }
+  // S = 2n entries' worth of counts.  Every moment below is an exact integer numerator over a
+  // power of S (no cancellation between rounded quantities).
+  const int S2 = 2 * n;
+  const double S = (double)S2, invS = 1.0 / S, invS2 = invS * invS;
+  const double ux = Ssum * invS;
+  const double ac = 2.0 * Sab * invS;
+  const double contrast = 2.0 * (double)(Sq - 2 * Sab) * invS;
+  const int vnum = S2 * Sq - Ssum * Ssum;                       // S^2 * var_x  (>= 0, exact)
+  const double sxx = vnum * invS2;
+  const double sxy = (double)(2 * Sab * S2 - Ssum * Ssum) * invS2;
+  const double ct = (double)(2 * (Sq + 2 * Sab) * S2 - 4 * Ssum * Ssum) * invS2;
+  const double da = 2.0 * Skd * invS;
+  const double dvar = (double)(2 * (Sq - 2 * Sab) * S2 - 4 * Skd * Skd) * invS2;
+  // scan the sorted keys: runs of equal key1 = merged matrix entries (length nn), runs of equal
+  // a+b = p_{x+y} bins, runs of equal key2 = p_{x-y} bins (the |i-j| table features are taken per run)
+  double cs = 0, cp = 0, idm = 0, idmn = 0, id = 0, idn = 0, inv = 0, lgE = 0, lgD = 0, lgS = 0;
+  int E2 = 0, cmax = 0, runK = 0, runS = 0, runD = 0;
+#pragma unroll
+  for (int i = 0; i < NP; i++) {
+    if (i < n) {
+      const int k1 = key1[i], ks = k1 >> 8, kd = k1 & 255, k2 = key2[i];
+      const double dn = (double)(ks * n - Ssum), d2 = dn * dn;   // (i+j-ux-uy) * n, an integer
+      cs += d2 * dn; cp += d2 * d2;
+      const int nx1 = (i + 1 < NP) ? key1[i + 1 < NP ? i + 1 : i] : -1;
+      const int nx2 = (i + 1 < NP) ? key2[i + 1 < NP ? i + 1 : i] : -1;
+      const bool last = (i + 1 == n);
+      runK++; runS++; runD++;
+      if (last || nx1 != k1) {                 // end of a merged-entry run
+        const int c = kd ? runK : 2 * runK;    // count of the matrix entry (both orders when i != j)
+        E2 += kd ? 2 * runK * runK : 4 * runK * runK;
+        if (c > cmax) cmax = c;
+        lgE += runK * T.log2t[c];
+        runK = 0;
+      }
+      if (last || (nx1 >> 8) != ks) { lgS += runS * T.log2t[2 * runS]; runS = 0; }
+      if (last || nx2 != k2) {                 // end of a |i-j| bin
+        const double r = (double)runD;
+        lgD += r * T.log2t[2 * runD];
+        idm += r * T.idm[k2]; idmn += r * T.idmn[k2]; id += r * T.id[k2]; idn += r * T.idn[k2]; inv += r * T.inv[k2];
+        runD = 0;
+      }
+    }
+  }
+  const double invn = 1.0 / n, invn2 = invn * invn;
+  const double lS = T.log2t[2 * n];
+  const double hxy = -2.0 * invS * (lgE - n * lS);
+  const double dent = -2.0 * invS * (lgD - n * lS);
+  const double sent = -2.0 * invS * (lgS - n * lS);
+  const double hx0 = nlev > 1 ? lS - rl * invS : 0.0;   // one level: exactly 0 (avoids 0/rounding in Imc1)
+  // HX = HY = hx0 and HXY1 = HXY2 = 2*hx0 (sum_ij p log2(px py) = sum_i px log2 px + sum_j py log2 py);
+  // the reference's "+eps" inside each log2 shifts these by < 1e-13 and is dropped consistently.
+  const double hx = hx0, hxy2 = 2.0 * hx0, hxy1 = hxy2;
+  double f[GLCM_NF];
+  f[G_Autocorrelation] = ac; f[G_JointAverage] = ux;
+  f[G_ClusterProminence] = cp * invn2 * invn2 * invn; f[G_ClusterShade] = cs * invn2 * invn2; f[G_ClusterTendency] = ct;
+  f[G_Contrast] = contrast;
+  f[G_Correlation] = (vnum == 0) ? 1.0 : sxy / (sxx + EPS);
+  f[G_DifferenceAverage] = da; f[G_DifferenceEntropy] = dent; f[G_DifferenceVariance] = dvar;
+  f[G_JointEnergy] = E2 * invS2; f[G_JointEntropy] = hxy;
+  f[G_Imc1] = (hx != 0) ? (hxy - hxy1) / hx : 0.0;
+  // exactly independent margins give HXY2 == HXY in the reference (value 0); here the two are
+  // built from different table sums, so "equal" means equal to rounding
+  const double dxy = hxy2 - hxy;
+  f[G_Imc2] = (fabs(dxy) < 1e-12) ? 0.0 : sqrt(1.0 - exp(-2.0 * dxy));
+  f[G_Idm] = 2.0 * idm * invS; f[G_Idmn] = 2.0 * idmn * invS; f[G_Id] = 2.0 * id * invS; f[G_Idn] = 2.0 * idn * invS;
+  f[G_InverseVariance] = 2.0 * inv * invS;
+  f[G_MaximumProbability] = cmax * invS; f[G_SumAverage] = 2.0 * ux; f[G_SumEntropy] = sent; f[G_SumSquares] = sxx;
   f[G_MCC] = mcc;
 #pragma unroll
   for (int k = 0; k < GLCM_NF; k++) if (k != G_Imc2) acc.sum[k] += f[k];
@@ -400,12 +403,8 @@ RB_HD uint32_t glcm_fast_voxel_phaseA(const uint8_t* w, int ws, uint32_t* eq, in
 #pragma unroll
   for (int p = 0; p < 27; p++) wl[p] = w[p * ws];
   RB_EQMASKS_27(wl, e);
-  uint32_t repmask = 0;
 #pragma unroll
-  for (int p = 0; p < 27; p++) {
-    eq[p * es] = e[p];
-    if (e[p] && (e[p] & ((1u << p) - 1)) == 0) repmask |= 1u << p;
-  }
+  for (int p = 0; p < 27; p++) eq[p * es] = e[p];
   GlcmAcc acc;
 #pragma unroll
   for (int k = 0; k < GLCM_NF; k++) acc.sum[k] = 0;
@@ -413,9 +412,9 @@ RB_HD uint32_t glcm_fast_voxel_phaseA(const uint8_t* w, int ws, uint32_t* eq, in
   // RB_ANGLE_SYNC: on the device the block re-converges before every angle so that its warps walk
   // the (large, fully unrolled) angle bodies together and share instruction-cache lines -- without
   // it the kernel is instruction-fetch bound (ncu: 15 "no_instruction" stall cycles per issue).
-  for (int s = 0; s < 3; s++) { RB_ANGLE_SYNC(); glcm_fast_angle<18>(w, ws, eq, es, repmask, T, s, P, acc); }
-  for (int s = 3; s < 9; s++) { RB_ANGLE_SYNC(); glcm_fast_angle<12>(w, ws, eq, es, repmask, T, s, P, acc); }
-  for (int s = 9; s < 13; s++) { RB_ANGLE_SYNC(); glcm_fast_angle<8>(w, ws, eq, es, repmask, T, s, P, acc); }
+  for (int s = 0; s < 3; s++) { RB_ANGLE_SYNC(); glcm_fast_angle<18>(w, ws, eq, es, T, s, P, acc); }
+  for (int s = 3; s < 9; s++) { RB_ANGLE_SYNC(); glcm_fast_angle<12>(w, ws, eq, es, T, s, P, acc); }
+  for (int s = 9; s < 13; s++) { RB_ANGLE_SYNC(); glcm_fast_angle<8>(w, ws, eq, es, T, s, P, acc); }
   *n_ok_out = acc.n_ok;
   if (tcls_out) *tcls_out = acc.tcls;
   const double inv = acc.n_ok ? 1.0 / acc.n_ok : NAN;

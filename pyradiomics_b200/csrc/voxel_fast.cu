@@ -258,11 +258,15 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
     long long need = (total + GF_THREADS - 1) / GF_THREADS, cap = (long long)sms * 16;
     const int grid = (int)(need < cap ? need : cap);
     static const int nt = getenv("B200_GLCM_NT") ? atoi(getenv("B200_GLCM_NT")) : 256;
+    static const int minb = getenv("B200_GLCM_MINB") ? atoi(getenv("B200_GLCM_MINB")) : 1;
+    const uint8_t* l8 = (const uint8_t*)lev;
     if (nt == 256) {
       long long need2 = (total + 255) / 256, cap2 = (long long)sms * 8;
-      glcm_fast_kernel<1, 256><<<(int)(need2 < cap2 ? need2 : cap2), 256, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
+      const int g2 = (int)(need2 < cap2 ? need2 : cap2);
+      if (minb >= 2) glcm_fast_kernel<2, 256><<<g2, 256, 0, st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
+      else glcm_fast_kernel<1, 256><<<g2, 256, 0, st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
     } else {
-      glcm_fast_kernel<2, 128><<<grid, 128, 0, st>>>((const uint8_t*)lev, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
+      glcm_fast_kernel<2, 128><<<grid, 128, 0, st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
     }
     RB_LAUNCH_CHECK();
     static const int solve_bps = getenv("B200_GLCM_SOLVE_BPS") ? atoi(getenv("B200_GLCM_SOLVE_BPS")) : 8;
