@@ -157,3 +157,17 @@ def test_host_extractor_chunks_and_halo_block():
     res2 = hx2.run(lev[3:10], msk[3:10], 32, 32)
     for c in ("glrlm", "ngtdm"):
         assert np.array_equal(res2[c].numpy(), voxel.voxel_features(c, dev, s, z0=4, z1=9).cpu().numpy()), c
+
+
+def test_sixteen_bit_levels_take_the_generic_kernels():
+    """Ng > 255 -> uint16 level volume -> generic kernels; against the oracle"""
+    rng = np.random.default_rng(8)
+    lev = rng.integers(250, 301, (7, 8, 9)).astype(np.int32)
+    lev[2, 3, 4] = 0
+    msk = lev != 0
+    levels = np.unique(lev[msk])
+    for cname in _lib.CLASSES:
+        got = _maps_host(cname, lev, int(levels.max()), len(levels))
+        ref = PL.extract(cname, lev, msk, voxelBased=True, binWidth=1)
+        for f, arr in ref.items():
+            assert_maps_close(got[f][msk], arr, f"u16/{cname}/{f}")
