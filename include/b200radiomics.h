@@ -174,6 +174,21 @@ int rb_recursive_gaussian_axis_dev(const void *in_dev, int in_is_f32, int Z, int
                                    const double *coef20, float *out_dev, double *scratch_dev, double scale,
                                    int accumulate, void *stream);
 
+/* ---- voxel-based first-order feature maps (the next plugin after the five
+ *      texture classes; reference radiomics/firstorder.py:40-474).  For every centre voxel of planes
+ *      [z0,z1): the 18 first-order features over its kernel window (radii rz,ry,rx per dimension: the
+ *      reference limits each to ROI-bbox size - 1 and to 0 in the force2D dimension), written like
+ *      rb_voxel_features_dev.  image_dev: raw intensities (dtype codes as rb_minmax_dev);
+ *      mask_dev: voxels that belong to kernels (NULL = all); centers_dev: voxels to compute (NULL =
+ *      mask); levels_dev: discretised levels (rb_pack_levels_dev) for Entropy / Uniformity.
+ *      Feature order = rb_firstorder_feature_name(0..17). */
+int rb_firstorder_num_features(void);
+const char *rb_firstorder_feature_name(int idx);
+int rb_firstorder_voxel_dev(const void *image_dev, int dtype, const uint8_t *mask_dev, const uint8_t *centers_dev,
+                            const void *levels_dev, int level_bytes, int Z, int Y, int X, int rz, int ry, int rx,
+                            double voxelArrayShift, double voxel_volume, double initValue, double *out_dev,
+                            long long out_feature_stride, int z0, int z1, int out_z0, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,13 @@ int swt_axis_launch(const double* in, int Z, int Y, int X, int axis, const doubl
 int recursive_gauss_launch(const void* in, int in_is_f32, int Z, int Y, int X, int axis, const double* coef20, float* out,
                            double* scratch, double scale, int accumulate, cudaStream_t st);
 
+int firstorder_launch(const void* img, int dtype, const uint8_t* mask, const uint8_t* centers, const void* lev,
+                      int level_bytes, int Z, int Y, int X, int rz, int ry, int rx, double shift, double voxel_volume,
+                      double init_value, double* out, long long fstride, int z0, int z1, int out_z0, cudaStream_t st);
+static const char* kFirstOrderNames[] = {"10Percentile", "90Percentile", "Energy", "Entropy", "InterquartileRange", "Kurtosis",
+  "Maximum", "MeanAbsoluteDeviation", "Mean", "Median", "Minimum", "Range", "RobustMeanAbsoluteDeviation", "RootMeanSquared",
+  "Skewness", "TotalEnergy", "Uniformity", "Variance"};
+
 static const char* kGlcmNames[] = {"Autocorrelation", "ClusterProminence", "ClusterShade", "ClusterTendency", "Contrast",
   "Correlation", "DifferenceAverage", "DifferenceEntropy", "DifferenceVariance", "Id", "Idm", "Idmn", "Idn", "Imc1", "Imc2",
   "InverseVariance", "JointAverage", "JointEnergy", "JointEntropy", "MCC", "MaximumProbability", "SumAverage", "SumEntropy",
@@ -258,6 +265,20 @@ int rb_recursive_gaussian_axis_dev(const void* in_dev, int in_is_f32, int Z, int
   if (axis < 0 || axis > 2) return fail(RB_ERR_ARG, "axis must be 0..2");
   return recursive_gauss_launch(in_dev, in_is_f32, Z, Y, X, axis, coef20, out_dev, scratch_dev, scale, accumulate,
                                 (cudaStream_t)stream);
+}
+
+int rb_firstorder_num_features(void) { return 18; }
+const char* rb_firstorder_feature_name(int idx) { return (idx < 0 || idx >= 18) ? NULL : kFirstOrderNames[idx]; }
+int rb_firstorder_voxel_dev(const void* image_dev, int dtype, const uint8_t* mask_dev, const uint8_t* centers_dev,
+                            const void* levels_dev, int level_bytes, int Z, int Y, int X, int rz, int ry, int rx,
+                            double voxelArrayShift, double voxel_volume, double initValue, double* out_dev,
+                            long long out_feature_stride, int z0, int z1, int out_z0, void* stream) {
+  if (dtype < 0 || dtype > 6) return fail(RB_ERR_ARG, "unknown dtype code %d", dtype);
+  if (level_bytes != 1 && level_bytes != 2) return fail(RB_ERR_ARG, "level_bytes must be 1 or 2");
+  if (rz < 0 || ry < 0 || rx < 0 || z0 < 0 || z1 > Z || z0 > z1) return fail(RB_ERR_ARG, "bad window / z range");
+  return firstorder_launch(image_dev, dtype, mask_dev, centers_dev, levels_dev, level_bytes, Z, Y, X, rz, ry, rx,
+                           voxelArrayShift, voxel_volume, initValue, out_dev, out_feature_stride, z0, z1, out_z0,
+                           (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -324,8 +324,102 @@ class RadiomicsNGTDM(RadiomicsFeaturesBase):
 
 _add_feature_getters(RadiomicsNGTDM, ["Busyness", "Coarseness", "Complexity", "Contrast", "Strength"])
 
+class RadiomicsFirstOrder(RadiomicsFeaturesBase):
+    """First-order statistics (reference radiomics/firstorder.py).  Voxel-
+    based: one fused CUDA kernel (rb_firstorder_voxel_dev) over the raw intensities + discretised
+    levels; segment-based: the ROI vector is reduced on the host like the reference does.
+
+    Deviation (documented in DESIGN.md): voxel-based Entropy / Uniformity histogram the SAME window as
+    the other features; the reference indexes its unpadded discretised array with padded coordinates
+    (firstorder.py:109), i.e. a window shifted by +kernelRadius, or raises IndexError."""
+    CLASS, MATRIX_ATTR = "firstorder", "_unused_matrix"
+    NAMES = ["10Percentile", "90Percentile", "Energy", "Entropy", "InterquartileRange", "Kurtosis", "Maximum",
+             "MeanAbsoluteDeviation", "Mean", "Median", "Minimum", "Range", "RobustMeanAbsoluteDeviation",
+             "RootMeanSquared", "Skewness", "TotalEnergy", "Uniformity", "Variance"]
+
+    def __init__(self, inputImage, inputMask, **kwargs):
+        self.voxelArrayShift = kwargs.get("voxelArrayShift", 0)
+        self.pixelSpacing = I.spacing_xyz(inputImage)
+        self._raw = I.as_array(inputImage)
+        super().__init__(inputImage, inputMask, **kwargs)
+        self.discretizedImageArray = self.imageArray
+        self.imageArray = self._raw
+
+    def _window_radii(self):
+        r = int(self.settings.get("kernelRadius", 1))
+        nd = self._raw.ndim
+        if self.masked:
+            idx = self.labelledVoxelCoordinates
+            size = idx.max(1) - idx.min(1) + 1
+        else:
+            size = np.array(self._raw.shape)
+        rad = [int(min(r, s - 1)) for s in size]
+        if self.settings.get("force2D", False):
+            rad[self.settings.get("force2Ddimension", 0)] = 0
+        return [0] * (3 - nd) + rad
+
+    def _calculateVoxels(self):
+        import ctypes as C
+        img = imageoperations._to_device(self._raw)
+        msk = imageoperations._to_device(self.maskArray)
+        lev = self._levels_dev
+        if img.ndim == 2:
+            img, msk, lev = img[None], msk[None], lev[None]
+        centers = None if self.masked else imageoperations._to_device(self._centerMask if self._centerMask.ndim == 3 else self._centerMask[None])
+        Z, Y, X = img.shape
+        rz, ry, rx = self._window_radii()
+        nf = _lib.lib().rb_firstorder_num_features()
+        out = torch.empty((nf, Z, Y, X), dtype=torch.float64, device=img.device)
+        vv = float(np.multiply.reduce(self.pixelSpacing))
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        _lib.check(_lib.lib().rb_firstorder_voxel_dev(
+            ptr(img), imageoperations._TORCH_DT[img.dtype], ptr(msk), ptr(centers), ptr(lev), voxel.level_bytes(lev), Z, Y, X,
+            rz, ry, rx, C.c_double(float(self.voxelArrayShift)), C.c_double(vv), C.c_double(float(self.settings.get("initValue", 0))),
+            ptr(out), C.c_longlong(out.stride(0)), 0, Z, 0, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "firstorder")
+        host = out.cpu().numpy()
+        for k, name in enumerate(self.NAMES):
+            if self.enabledFeatures.get(name):
+                arr = host[k] if self._raw.ndim == 3 else host[k][0]
+                self.featureValues[name] = I.like(self.inputImage, np.ascontiguousarray(arr))
+
+    def _initCalculation(self, voxelCoordinates=None):
+        pass
+
+    def _segment_features(self):
+        x = np.sort(self._raw[self.maskArray].astype(np.float64))
+        n = x.size
+        sh = x + self.voxelArrayShift
+        en = float(np.sum(sh ** 2))
+        mean = float(x.mean())
+        pct = lambda q: float(np.percentile(x, q))
+        _, cnt = np.unique(self.discretizedImageArray[self.maskArray], return_counts=True)
+        p = cnt / cnt.sum()
+        d = x - mean
+        m2, m3, m4 = float(np.mean(d ** 2)), float(np.mean(d ** 3)), float(np.mean(d ** 4))
+        m2s = 1.0 if m2 == 0 else m2
+        p10, p90 = pct(10), pct(90)
+        kept = x[(x >= p10) & (x <= p90)]
+        return {
+            "10Percentile": p10, "90Percentile": p90, "Energy": en, "Entropy": float(-np.sum(p * np.log2(p + MF.EPS))),
+            "InterquartileRange": pct(75) - pct(25), "Kurtosis": m4 / m2s ** 2, "Maximum": float(x[-1]),
+            "MeanAbsoluteDeviation": float(np.mean(np.abs(d))), "Mean": mean, "Median": float(np.median(x)),
+            "Minimum": float(x[0]), "Range": float(x[-1] - x[0]),
+            "RobustMeanAbsoluteDeviation": float(np.mean(np.abs(kept - kept.mean()))), "RootMeanSquared": float(np.sqrt(en / n)),
+            "Skewness": m3 / m2s ** 1.5, "TotalEnergy": en * float(np.multiply.reduce(self.pixelSpacing)),
+            "Uniformity": float(np.sum(p ** 2)), "Variance": m2,
+        }
+
+    def _value(self, name):
+        return np.float64(self._segment_features()[name])
+
+
+_add_feature_getters(RadiomicsFirstOrder, RadiomicsFirstOrder.NAMES,
+                     deprecated=[("StandardDeviation", "the square root of Variance")])
+
 FEATURE_CLASSES = {"glcm": RadiomicsGLCM, "glrlm": RadiomicsGLRLM, "glszm": RadiomicsGLSZM, "gldm": RadiomicsGLDM,
                    "ngtdm": RadiomicsNGTDM}
+# next row of the hot-path table (SURVEY.md section 8f): registered by install() as well
+NEXT_CLASSES = {"firstorder": RadiomicsFirstOrder}
 
 
 def install(radiomics_module=None):
@@ -336,7 +430,7 @@ def install(radiomics_module=None):
 
     rad = radiomics_module or importlib.import_module("radiomics")
     classes = rad.getFeatureClasses()
-    for name, cls in FEATURE_CLASSES.items():
+    for name, cls in {**FEATURE_CLASSES, **NEXT_CLASSES}.items():
         classes[name] = cls
     rad.cMatrices = cmatrices
     for mod in ("glcm", "glrlm", "glszm", "gldm", "ngtdm", "firstorder"):

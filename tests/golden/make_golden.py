@@ -149,7 +149,56 @@ def voxmat_goldens():
     np.savez_compressed(os.path.join(HERE, "voxmat_small.npz"), **out)
 
 
+def firstorder_goldens():
+    """first-order class: baseline CSV columns (segment mode) and a
+    voxel-mode run of the reference.  The voxel volume keeps the ROI >= 2*kernelRadius away from the
+    far border because the reference indexes its unpadded discretised array with padded coordinates
+    (firstorder.py:109) and raises IndexError otherwise; for the same reason its voxel-mode Entropy /
+    Uniformity (shifted histogram window) are NOT stored as goldens."""
+    from radiomics import firstorder
+    rows = list(csv.reader(open(os.path.join(rh.REF_ROOT, "data", "baseline", "baseline_firstorder.csv"))))
+    header = rows[0]
+    byname = {r[0]: r for r in rows}
+    expect = {}
+    for col in range(1, len(header)):
+        test = header[col]
+        case = byname["diagnostics_Configuration_TestCase"][col]
+        settings = ast.literal_eval(byname["diagnostics_Configuration_Settings"][col])
+        if any(settings.get(k) not in (None, False, [], 0) for k in PRE_KEYS):
+            continue
+        kw = {k: v for k, v in settings.items() if k in HOT_KEYS | {"voxelArrayShift"} and v is not None}
+        feats = {r[0].split("_", 2)[2]: float(r[col]) for r in rows if r[0].startswith("original_firstorder_")}
+        img, m, sp = rh.load_case(case)
+        got = firstorder.RadiomicsFirstOrder(sitk.Image(img, sp), sitk.Image(m.astype(np.uint8), sp), **kw).execute()
+        worst = max(abs(float(got[f]) - v) / max(abs(v), 1e-300) for f, v in feats.items())
+        assert worst < 1e-9, (test, worst)
+        expect[test] = {"case": case, "settings": kw, "features": feats}
+        print("segment firstorder", test, "ok rel", worst)
+    json.dump(expect, open(os.path.join(HERE, "segment_expect_firstorder.json"), "w"), indent=0, sort_keys=True)
+    rng = np.random.default_rng(21)
+    z, y, x = np.meshgrid(np.arange(10), np.arange(11), np.arange(12), indexing="ij")
+    img = (300 + 120 * np.sin(z / 2.0) + 90 * np.cos(y / 3.0) + 60 * np.sin(x / 2.5) + rng.normal(0, 25, z.shape)).astype(np.int16)
+    out = {"image": img}
+    for name, r, msk in (("r1", 1, (rng.random(z.shape) > 0.2) & (z < 8) & (y < 9) & (x < 10)),
+                         ("r2", 2, (rng.random(z.shape) > 0.3) & (z < 6) & (y < 7) & (x < 8))):
+        sp = (0.8, 0.9, 2.0)
+        obj = firstorder.RadiomicsFirstOrder(sitk.Image(img, sp), sitk.Image(msk.astype(np.uint8), sp), voxelBased=True,
+                                             kernelRadius=r, binWidth=25, voxelArrayShift=100)
+        res = obj.execute()
+        out[f"{name}_mask"] = msk
+        for f, im in res.items():
+            if f not in ("Entropy", "Uniformity"):
+                out[f"{name}_{f}"] = sitk.GetArrayFromImage(im)
+        print("voxel firstorder", name, len(res))
+    out["spacing"] = np.array((0.8, 0.9, 2.0))
+    np.savez_compressed(os.path.join(HERE, "voxel_firstorder.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--firstorder-only" in sys.argv:
+        firstorder_goldens()
+        sys.exit(0)
     segment_goldens()
+    firstorder_goldens()
     voxmat_goldens()
     voxel_goldens()

@@ -18,6 +18,8 @@ def voxel_goldens():
     out = []
     for fn in sorted(glob.glob(os.path.join(GOLDEN, "voxel_*.npz"))):
         z = np.load(fn)
+        if "settings" not in z.files:        # e.g. voxel_firstorder.npz has its own tests
+            continue
         out.append((os.path.basename(fn)[6:-4], z, json.loads(str(z["settings"]))))
     return out
 

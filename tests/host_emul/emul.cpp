@@ -126,3 +126,26 @@ extern "C" int emul_small_fast(int cls, const uint16_t* lev, int Z, int Y, int X
   delete T;
   return 0;
 }
+
+#include "../../pyradiomics_b200/csrc/firstorder.cuh"
+// first-order window statistics on the host: img (double), mask (window membership), lev (levels)
+extern "C" int emul_firstorder(const double* img, const uint8_t* mask, const uint16_t* lev, int Z, int Y, int X, int rz,
+                               int ry, int rx, double shift, double vv, double* out) {
+  const long long nvox = (long long)Z * Y * X;
+  for (int z = 0; z < Z; z++) for (int y = 0; y < Y; y++) for (int x = 0; x < X; x++) {
+    long long i = ((long long)z * Y + y) * X + x;
+    if (!mask[i]) { for (int k = 0; k < FIRSTORDER_NF; k++) out[k * nvox + i] = 0; continue; }
+    double xs[343]; uint16_t w[343]; int n = 0, wn = 0; double f[FIRSTORDER_NF];
+    for (int dz = -rz; dz <= rz; dz++) for (int dy = -ry; dy <= ry; dy++) for (int dx = -rx; dx <= rx; dx++, wn++) {
+      int zz = z + dz, yy = y + dy, xx = x + dx;
+      w[wn] = 0;
+      if (zz < 0 || zz >= Z || yy < 0 || yy >= Y || xx < 0 || xx >= X) continue;
+      long long j = ((long long)zz * Y + yy) * X + xx;
+      if (!mask[j]) continue;
+      xs[n++] = img[j]; w[wn] = lev[j];
+    }
+    firstorder_voxel<343>(xs, n, w, wn, shift, vv, f);
+    for (int k = 0; k < FIRSTORDER_NF; k++) out[k * nvox + i] = f[k];
+  }
+  return 0;
+}

@@ -84,3 +84,26 @@ def test_device_math_on_host_matches_reference_maps(emul, name, z, kw):
         assert rc == 0
         for k, f in enumerate(NAMES[cname]):
             assert_maps_close(out[k], ref_map(z, cname, f), f"{name}/{cname}/{f}", rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("name,r", [("r1", 1), ("r2", 2)])
+def test_firstorder_device_math_on_host(emul, name, r):
+    """first-order window statistics (csrc/firstorder.cuh) against the reference's voxel-mode run"""
+    import firstorder_np as FO
+    import pipeline as PL
+    z = np.load(os.path.join(HERE, "golden", "voxel_firstorder.npz"))
+    img, m = z["image"], z[name + "_mask"]
+    lev, _, _, _ = PL.bin_image(img, m, 25)
+    lev16 = np.ascontiguousarray(np.where(m, lev, 0), dtype=np.uint16)
+    imgd = np.ascontiguousarray(img, dtype=np.float64)
+    mk = np.ascontiguousarray(m, dtype=np.uint8)
+    Zs, Ys, Xs = img.shape
+    out = np.zeros((18, Zs, Ys, Xs))
+    emul.emul_firstorder(imgd.ctypes.data_as(C.c_void_p), mk.ctypes.data_as(C.c_void_p), lev16.ctypes.data_as(C.c_void_p),
+                         Zs, Ys, Xs, r, r, r, C.c_double(100.0), C.c_double(float(np.prod(z["spacing"]))),
+                         out.ctypes.data_as(C.c_void_p))
+    ref = FO.extract(img, m, voxelBased=True, spacing_xyz=z["spacing"], kernelRadius=r, binWidth=25, voxelArrayShift=100)
+    for k, f in enumerate(FO.NAMES):
+        assert np.allclose(out[k][m], ref[f], rtol=1e-10, atol=1e-9), f
+        if f not in ("Entropy", "Uniformity"):
+            assert np.allclose(out[k][m], z[f"{name}_{f}"][m], rtol=1e-9, atol=1e-8), f

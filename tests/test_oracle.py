@@ -127,3 +127,22 @@ def test_pipeline_reproduces_reference_voxel_maps(name, z, kw):
         got = PL.extract(cname, z["image"], m, voxelBased=True, spacing_zyx=z["spacing"][::-1], **kw)
         for f, arr in got.items():
             assert_maps_close(arr, ref_map(z, cname, f)[m], f"{name}/{cname}/{f}", rtol=1e-8, atol=1e-10)
+
+
+def test_firstorder_oracle_reproduces_reference():
+    """oracle/firstorder_np.py against data/baseline/baseline_firstorder.csv and the reference's voxel run"""
+    import firstorder_np as FO
+    cases = np.load(os.path.join(GOLDEN, "segment_cases.npz"))
+    exp = json.load(open(os.path.join(GOLDEN, "segment_expect_firstorder.json")))
+    for test, e in exp.items():
+        c = e["case"]
+        got = FO.extract(cases[c + "_image"], cases[c + "_mask"], spacing_xyz=cases[c + "_spacing"], **e["settings"])
+        for f, v in e["features"].items():
+            assert abs(got[f] - v) <= 1e-10 * max(abs(v), 1e-12), (test, f)
+    z = np.load(os.path.join(GOLDEN, "voxel_firstorder.npz"))
+    for name, r in (("r1", 1), ("r2", 2)):
+        m = z[name + "_mask"]
+        got = FO.extract(z["image"], m, voxelBased=True, spacing_xyz=z["spacing"], kernelRadius=r, binWidth=25, voxelArrayShift=100)
+        for f in FO.NAMES:
+            if f not in ("Entropy", "Uniformity"):
+                assert np.allclose(got[f], z[f"{name}_{f}"][m], rtol=1e-10, atol=1e-9), (name, f)

@@ -205,3 +205,36 @@ def test_segment_batch_shards_cases(seg):
         got = (r0 if k % 2 == 0 else r1)[k]["ngtdm"]
         for f, v in expect["ngtdm"][c]["features"].items():
             assert abs(got[f] - v) <= 1e-7 * abs(v)
+
+
+# ------------------------------------------------------------------------------ first-order (next row)
+def test_firstorder_segment_matches_reference_baseline(seg):
+    cases, _ = seg
+    exp = json.load(open(os.path.join(GOLDEN, "segment_expect_firstorder.json")))
+    for test, e in exp.items():
+        c = e["case"]
+        obj = FC.RadiomicsFirstOrder(I.ArrayImage(cases[c + "_image"], cases[c + "_spacing"]),
+                                     I.ArrayImage(cases[c + "_mask"].astype(np.uint8), cases[c + "_spacing"]), **e["settings"])
+        got = obj.execute()
+        assert set(got) == set(e["features"])
+        for f, v in e["features"].items():
+            assert abs(float(got[f]) - v) <= 1e-9 * max(abs(v), 1e-12), (test, f, float(got[f]), v)
+
+
+@pytest.mark.parametrize("name,r", [("r1", 1), ("r2", 2)])
+def test_firstorder_voxel_maps(name, r):
+    """16 features against the reference's own voxel-mode run; all 18 against the oracle (Entropy /
+    Uniformity of the reference use a shifted window -- firstorder.py:109 -- and are not goldens)"""
+    import firstorder_np as FO
+    z = np.load(os.path.join(GOLDEN, "voxel_firstorder.npz"))
+    m = z[name + "_mask"]
+    got = FC.RadiomicsFirstOrder(I.ArrayImage(z["image"], z["spacing"]), I.ArrayImage(m.astype(np.uint8), z["spacing"]),
+                                 voxelBased=True, kernelRadius=r, binWidth=25, voxelArrayShift=100).execute()
+    ref = FO.extract(z["image"], m, voxelBased=True, spacing_xyz=z["spacing"], kernelRadius=r, binWidth=25, voxelArrayShift=100)
+    assert list(got) == FO.NAMES
+    for f in FO.NAMES:
+        arr = I.as_array(got[f])
+        assert np.allclose(arr[m], ref[f], rtol=1e-9, atol=1e-9), f
+        assert (arr[~m] == 0).all()
+        if f not in ("Entropy", "Uniformity"):
+            assert np.allclose(arr[m], z[f"{name}_{f}"][m], rtol=1e-5, atol=1e-8), f
