@@ -40,6 +40,9 @@ constexpr int GF_KT = 256;        // |a-b| tables
 #ifndef RB_LZ_T
 #define RB_LZ_T float
 #endif
+#ifndef GF_LOCAL_REORTH
+#define GF_LOCAL_REORTH 0
+#endif
 #ifndef GF_LANCZOS_ATTEMPTS
 #define GF_LANCZOS_ATTEMPTS 1
 #endif
@@ -53,6 +56,7 @@ struct GlcmFastTables {
   double log2t[GF_LOGT];          // log2(c), log2t[0] = 0 (never used with weight)
   double idm[GF_KT], idmn[GF_KT], id[GF_KT], idn[GF_KT], inv[GF_KT];   // by k = |i-j|
   double lz0[19], lz1[19];        // Lanczos start vectors (see kLanczosStart0/1)
+  double rsq[GF_LOGT];            // 1 / sqrt(c) for the small integer row sums
 };
 
 // Lanczos start vectors: two fixed tables of unstructured components in [0.25, 1.25) (drawn once
@@ -87,8 +91,8 @@ inline void glcm_fast_build_tables(GlcmFastTables& T, int Ng) {
       slot++;
     }
   for (int i = 0; i < 19; i++) { T.lz0[i] = kLanczosStart0[i]; T.lz1[i] = kLanczosStart1[i]; }
-  T.log2t[0] = 0;
-  for (int c = 1; c < GF_LOGT; c++) T.log2t[c] = log2((double)c);
+  T.log2t[0] = 0; T.rsq[0] = 0;
+  for (int c = 1; c < GF_LOGT; c++) { T.log2t[c] = log2((double)c); T.rsq[c] = 1.0 / sqrt((double)c); }
   for (int d = 0; d < GF_KT; d++) {
     double kk = d;
     T.idm[d] = 1.0 / (1.0 + kk * kk);
@@ -128,10 +132,11 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const GlcmFastTable
     v1[i] += 1.0; v1[j] += 1.0;
   }
   if (n < 2) return 0.0;
+  // row sums are small integers (<= 36): 1/sqrt from a table
   double S = 0, tr = 0;
   for (int i = 0; i < n; i++) S += v1[i];
   for (int t = 0; t < ne; t++) {
-    ew[t] = 1.0 / sqrt(v1[ei[t]] * v1[ej[t]]);
+    ew[t] = T.rsq[(int)v1[ei[t]]] * T.rsq[(int)v1[ej[t]]];
     if (ei[t] == ej[t]) tr += 2.0 * ew[t];      // trace of M
   }
   if (n == 2) return fabs(tr - 1.0);          // eigenvalues are 1 and trace - 1
@@ -167,11 +172,17 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const GlcmFastTable
       for (int i = 0; i < n; i++) alpha += q1[i] * z[i];
       double dv = 0;
       for (int i = 0; i < n; i++) { z[i] -= alpha * q1[i] + beta * q0[i]; dv += z[i] * v1[i]; }
+#if GF_LOCAL_REORTH
       // re-orthogonalise against the deflated vector and the last two Lanczos vectors
       double c1 = 0, c0 = 0;
       for (int i = 0; i < n; i++) { z[i] -= dv * v1[i]; c1 += z[i] * q1[i]; c0 += z[i] * q0[i]; }
       double nb = 0;
       for (int i = 0; i < n; i++) { z[i] -= c1 * q1[i] + c0 * q0[i]; nb += z[i] * z[i]; }
+#else
+      // keep the iterate orthogonal to the deflated (known) eigenvector
+      double nb = 0;
+      for (int i = 0; i < n; i++) { const double zi = z[i] - dv * v1[i]; z[i] = zi; nb += zi * zi; }
+#endif
       d[m] = alpha; m++;
       nb = sqrt(nb);
       if (nb < 1e-10 || j == n - 2) break;       // invariant subspace reached / basis complete

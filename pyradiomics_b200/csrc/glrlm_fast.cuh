@@ -12,10 +12,10 @@
 namespace rb {
 
 struct GlrlmFastTables {
-  uint32_t step[GF_NA][27];   // nxt | prv << 8 | pprv << 16 (window position, 31 = outside the window)
   uint32_t VA[GF_NA], VA2[GF_NA];   // positions whose successor / second successor is inside the window
   uint8_t delta[GF_NA];       // index offset of the angle (dz*9 + dy*3 + dx > 0 for the 13 angles)
   double log2t[32];
+  double clog2[32];           // c * log2(c)
   double inv2[256];           // 1 / level^2
 };
 
@@ -32,25 +32,38 @@ inline void glrlm_fast_build_tables(GlrlmFastTables& T) {
         const int z2 = z + m * ang[a][0], y2 = y + m * ang[a][1], x2 = x + m * ang[a][2];
         return (z2 < 0 || z2 > 2 || y2 < 0 || y2 > 2 || x2 < 0 || x2 > 2) ? 31 : z2 * 9 + y2 * 3 + x2;
       };
-      const int nx = pos(1), nx2 = pos(2), pv = pos(-1), ppv = pos(-2);
-      T.step[a][v] = (uint32_t)nx | (uint32_t)pv << 8 | (uint32_t)ppv << 16;
+      const int nx = pos(1), nx2 = pos(2);
       if (nx != 31) T.VA[a] |= 1u << v;
       if (nx2 != 31) T.VA2[a] |= 1u << v;
     }
   }
   T.log2t[0] = 0;
-  for (int c = 1; c < 32; c++) T.log2t[c] = log2((double)c);
+  T.clog2[0] = 0;
+  for (int c = 1; c < 32; c++) { T.log2t[c] = log2((double)c); T.clog2[c] = c * log2((double)c); }
   T.inv2[0] = 0;
   for (int g = 1; g < 256; g++) T.inv2[g] = 1.0 / ((double)g * g);
 }
 
-// wl: the 27 window levels (registers), out: 16 features in GlrlmF order
+// wl: the 27 window levels (registers), out: 16 features in GlrlmF order.
+//
+// Bit-parallel formulation: with E = equality mask of one level class and d = the angle's index
+// offset, the voxels whose successor along the angle is in the window AND of the same class are
+// NS = OR_classes( E & (E >> d) & VA ).  Then run ends = M & ~NS, "previous voxel is the same class"
+// PS = NS << d, "previous two" PS2 = PS & (PS << d), and the run-length-1/2/3 end masks follow with
+// three more logic ops -- for all 27 voxels at once.  Everything else is popcounts per class.
 RB_HD void glrlm_fast_voxel(const int* wl, const GlrlmFastTables& T, double* out) {
   uint32_t e[27];
   RB_EQMASKS_27(wl, e);
   uint32_t M = 0;
+  // compact the level classes (data-dependent count): mask + level of each distinct level
+  uint32_t cls[27];
+  int clg[27];
+  int nl = 0;
 #pragma unroll
-  for (int v = 0; v < 27; v++) if (wl[v]) M |= 1u << v;
+  for (int v = 0; v < 27; v++) {
+    if (wl[v]) M |= 1u << v;
+    if (e[v] && (e[v] & ((1u << v) - 1)) == 0) { cls[nl] = e[v]; clg[nl] = wl[v]; nl++; }
+  }
   const int Np = RB_POPC(M);
   double sum[GLRLM_NF];
 #pragma unroll
@@ -58,37 +71,26 @@ RB_HD void glrlm_fast_voxel(const int* wl, const GlrlmFastTables& T, double* out
   int nang = 0;
   for (int a = 0; a < GF_NA; a++) {
     const int d = T.delta[a];
+    const uint32_t VA = T.VA[a];
     // cmatrices.c:524-534: an angle none of whose lines holds two masked voxels is dropped
-    if (!(((M & T.VA[a]) & (M >> d)) | ((M & T.VA2[a]) & (M >> (2 * d))))) continue;
-    uint32_t ENDS = 0, L1 = 0, L2 = 0;
-    int n1 = 0, n2 = 0, n3 = 0, B1 = 0, B2 = 0, B3 = 0, C = 0;
-    double A1 = 0, A2 = 0, A3 = 0;
-#pragma unroll
-    for (int v = 0; v < 27; v++) {
-      const uint32_t ev = e[v];
-      const uint32_t st = T.step[a][v];
-      const bool is_end = ev != 0 && !((ev >> (st & 31)) & 1u);
-      if (is_end) {
-        const uint32_t ps = (ev >> ((st >> 8) & 31)) & 1u, pps = ps & ((ev >> ((st >> 16) & 31)) & 1u);
-        const int g = wl[v], g2 = g * g;
-        const double ig = T.inv2[g];
-        ENDS |= 1u << v;
-        C += g;
-        if (!ps) { L1 |= 1u << v; n1++; B1 += g2; A1 += ig; }
-        else if (!pps) { L2 |= 1u << v; n2++; B2 += g2; A2 += ig; }
-        else { n3++; B3 += g2; A3 += ig; }
-      }
-    }
-    const uint32_t L3 = ENDS & ~(L1 | L2);
-    int sg = 0;
-    double lg = 0;
-#pragma unroll
-    for (int v = 0; v < 27; v++) {
-      if (ENDS >> v & 1u) {
-        sg += RB_POPC(e[v] & ENDS);
-        const uint32_t Lm = (L1 >> v & 1u) ? L1 : (L2 >> v & 1u) ? L2 : L3;
-        lg += T.log2t[RB_POPC(e[v] & Lm)];
-      }
+    if (!(((M & VA) & (M >> d)) | ((M & T.VA2[a]) & (M >> (2 * d))))) continue;
+    uint32_t NS = 0;
+    for (int k = 0; k < nl; k++) NS |= cls[k] & (cls[k] >> d);
+    NS &= VA;
+    const uint32_t ENDS = M & ~NS, PS = NS << d, PS2 = PS & (PS << d);
+    const uint32_t L1 = ENDS & ~PS, L2 = ENDS & PS & ~PS2, L3 = ENDS & PS2;
+    const int n1 = RB_POPC(L1), n2 = RB_POPC(L2), n3 = RB_POPC(L3);
+    int B1 = 0, B2 = 0, B3 = 0, C = 0, sg = 0;
+    double A1 = 0, A2 = 0, A3 = 0, lg = 0;
+    for (int k = 0; k < nl; k++) {
+      const uint32_t E = cls[k];
+      const int c1 = RB_POPC(E & L1), c2 = RB_POPC(E & L2), c3 = RB_POPC(E & L3), ce = c1 + c2 + c3;
+      const int g = clg[k], g2 = g * g;
+      const double ig = T.inv2[g];
+      sg += ce * ce; C += ce * g;
+      B1 += c1 * g2; B2 += c2 * g2; B3 += c3 * g2;
+      A1 += c1 * ig; A2 += c2 * ig; A3 += c3 * ig;
+      lg += T.clog2[c1] + T.clog2[c2] + T.clog2[c3];
     }
     const int Nr = n1 + n2 + n3;
     const double invNr = 1.0 / Nr, invNr2 = invNr * invNr;
