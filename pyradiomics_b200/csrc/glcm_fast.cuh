@@ -41,7 +41,7 @@ constexpr int GF_KT = 256;        // |a-b| tables
 #define RB_LZ_T float
 #endif
 #ifndef GF_LOCAL_REORTH
-#define GF_LOCAL_REORTH 0
+#define GF_LOCAL_REORTH 1
 #endif
 #ifndef GF_LANCZOS_ATTEMPTS
 #define GF_LANCZOS_ATTEMPTS 1
