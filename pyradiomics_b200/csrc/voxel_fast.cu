@@ -363,8 +363,11 @@ int glrlm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& 
 }
 
 // ------------------------------------------------------------------ GLSZM / GLDM / NGTDM fast paths
-template <int CLS>
-__global__ void __launch_bounds__(128)
+// SYNC: block-uniform tiles with a barrier per tile, so the block's warps stream the (large,
+// straight-line) GLDM / NGTDM bodies together and share instruction-cache lines (ncu showed 2.3
+// "no_instruction" stall cycles per issue for NGTDM with free-running warps).
+template <int CLS, int NT, bool SYNC>
+__global__ void __launch_bounds__(NT)
 small_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ centers,
                   const __grid_constant__ VoxParams P, const SmallFastTables* __restrict__ Tg,
                   double* __restrict__ out, long long fstride, int z0, int z1, int out_z0) {
@@ -372,20 +375,25 @@ small_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ c
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(Tg);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
-    for (int i = threadIdx.x; i < (int)(sizeof(SmallFastTables) / 4); i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(SmallFastTables) / 4); i += NT) dst[i] = src[i];
   }
   __syncthreads();
   constexpr int NF = CLS == C_GLSZM ? GLSZM_NF : CLS == C_GLDM ? GLDM_NF : NGTDM_NF;
   const long long plane = (long long)P.Y * P.X;
   const long long total = (long long)(z1 - z0) * plane;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int z = z0 + (int)(t / plane);
-    const int rem = (int)(t % plane);
+  const long long ntiles = (total + NT - 1) / NT;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (SYNC) __syncthreads();
+    const long long t = tile * NT + threadIdx.x;
+    const bool live = t < total;
+    if (!SYNC && !live) continue;
+    const int z = z0 + (int)((live ? t : 0) / plane);
+    const int rem = (int)((live ? t : 0) % plane);
     const int y = rem / P.X, x = rem % P.X;
     const long long vi = (long long)z * P.sz + (long long)y * P.sy + x;
     const long long oi = (long long)(z - out_z0) * plane + rem;
-    const bool is_center = centers ? centers[(long long)z * plane + rem] != 0 : lev[vi] != 0;
-    if (!is_center) {
+    const bool is_center = live && (centers ? centers[(long long)z * plane + rem] != 0 : lev[vi] != 0);
+    if (!SYNC && !is_center) {
 #pragma unroll
       for (int k = 0; k < NF; k++) out[k * fstride + oi] = P.init_value;
       continue;
@@ -400,7 +408,7 @@ small_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ c
 #pragma unroll
           for (int dx = -1; dx <= 1; dx++, p++) {
             const int zz = z + dz, yy = y + dy, xx = x + dx;
-            const bool in = zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
+            const bool in = is_center && zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
             wl[p] = in ? lev[vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : 0;
           }
     }
@@ -408,8 +416,9 @@ small_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ c
     if (CLS == C_GLSZM) glszm_fast_voxel(wl, T, f);
     else if (CLS == C_GLDM) gldm_fast_voxel(wl, P.alpha, T, f);
     else ngtdm_fast_voxel(wl, T, f);
+    if (!live) continue;
 #pragma unroll
-    for (int k = 0; k < NF; k++) out[k * fstride + oi] = f[k];
+    for (int k = 0; k < NF; k++) out[k * fstride + oi] = is_center ? f[k] : P.init_value;
   }
 }
 
@@ -444,12 +453,25 @@ int small_fast_launch(int cls, const void* lev, const uint8_t* centers, const Vo
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long long need = (total + 127) / 128, cap = (long long)sms * 32;
-  const int grid = (int)(need < cap ? need : cap);
   const uint8_t* l8 = (const uint8_t*)lev;
-  if (cls == C_GLSZM) small_fast_kernel<C_GLSZM><<<grid, 128, 0, st>>>(l8, centers, P, T, out, fstride, z0, z1, out_z0);
-  else if (cls == C_GLDM) small_fast_kernel<C_GLDM><<<grid, 128, 0, st>>>(l8, centers, P, T, out, fstride, z0, z1, out_z0);
-  else small_fast_kernel<C_NGTDM><<<grid, 128, 0, st>>>(l8, centers, P, T, out, fstride, z0, z1, out_z0);
+  static const int mode = getenv("B200_SMALL_MODE") ? atoi(getenv("B200_SMALL_MODE")) : 1;   // 0 free-running, 1 sync/128, 2 sync/256
+  if (cls == C_GLSZM || mode == 0) {
+    long long need = (total + 127) / 128, cap = (long long)sms * 32;
+    const int grid = (int)(need < cap ? need : cap);
+    if (cls == C_GLSZM) small_fast_kernel<C_GLSZM, 128, false><<<grid, 128, 0, st>>>(l8, centers, P, T, out, fstride, z0, z1, out_z0);
+    else if (cls == C_GLDM) small_fast_kernel<C_GLDM, 128, false><<<grid, 128, 0, st>>>(l8, centers, P, T, out, fstride, z0, z1, out_z0);
+    else small_fast_kernel<C_NGTDM, 128, false><<<grid, 128, 0, st>>>(l8, centers, P, T, out, fstride, z0, z1, out_z0);
+  } else if (mode == 1) {
+    long long need = (total + 127) / 128, cap = (long long)sms * 32;
+    const int grid = (int)(need < cap ? need : cap);
+    if (cls == C_GLDM) small_fast_kernel<C_GLDM, 128, true><<<grid, 128, 0, st>>>(l8, centers, P, T, out, fstride, z0, z1, out_z0);
+    else small_fast_kernel<C_NGTDM, 128, true><<<grid, 128, 0, st>>>(l8, centers, P, T, out, fstride, z0, z1, out_z0);
+  } else {
+    long long need = (total + 255) / 256, cap = (long long)sms * 16;
+    const int grid = (int)(need < cap ? need : cap);
+    if (cls == C_GLDM) small_fast_kernel<C_GLDM, 256, true><<<grid, 256, 0, st>>>(l8, centers, P, T, out, fstride, z0, z1, out_z0);
+    else small_fast_kernel<C_NGTDM, 256, true><<<grid, 256, 0, st>>>(l8, centers, P, T, out, fstride, z0, z1, out_z0);
+  }
   RB_LAUNCH_CHECK();
   return RB_OK;
 }
