@@ -43,6 +43,12 @@ constexpr int GF_KT = 256;        // |a-b| tables
 #ifndef GF_LOCAL_REORTH
 #define GF_LOCAL_REORTH 1
 #endif
+#ifndef GF_EXTRA_STEPS
+#define GF_EXTRA_STEPS 3     // float-stored Lanczos vectors lose orthogonality: n-1 steps are not always enough (6e-5 misses seen); +3 steps -> <= 3e-7 over 5e5 windows
+#endif
+#ifndef GF_BREAKDOWN
+#define GF_BREAKDOWN 1e-10
+#endif
 #ifndef GF_LANCZOS_ATTEMPTS
 #define GF_LANCZOS_ATTEMPTS 1
 #endif
@@ -157,11 +163,12 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const GlcmFastTable
     for (int i = 0; i < n; i++) { q1[i] -= dot * v1[i]; nrm += q1[i] * q1[i]; q0[i] = 0; }
     nrm = 1.0 / sqrt(nrm);
     for (int i = 0; i < n; i++) q1[i] *= nrm;
-    double d[19], e[19];
+    double d[19 + GF_EXTRA_STEPS], e[19 + GF_EXTRA_STEPS];
     double beta = 0;
     int m = 0;
     e[0] = 0;
-    for (int j = 0; j < n - 1; j++) {
+    const int jmax = n > 4 ? n - 2 + GF_EXTRA_STEPS : n - 2;
+    for (int j = 0; j <= jmax; j++) {
       for (int i = 0; i < n; i++) z[i] = 0;
       for (int t = 0; t < ne; t++) {
         const int a = ei[t], b = ej[t];
@@ -185,7 +192,7 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const GlcmFastTable
 #endif
       d[m] = alpha; m++;
       nb = sqrt(nb);
-      if (nb < 1e-10 || j == n - 2) break;       // invariant subspace reached / basis complete
+      if (nb < GF_BREAKDOWN || j == jmax) break;       // invariant subspace reached / basis complete
       e[m] = nb; beta = nb;
       const double inb = 1.0 / nb;
       for (int i = 0; i < n; i++) { q0[i] = q1[i]; q1[i] = z[i] * inb; }

@@ -454,7 +454,8 @@ int small_fast_launch(int cls, const void* lev, const uint8_t* centers, const Vo
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const uint8_t* l8 = (const uint8_t*)lev;
-  static const int mode = getenv("B200_SMALL_MODE") ? atoi(getenv("B200_SMALL_MODE")) : 1;   // 0 free-running, 1 sync/128, 2 sync/256
+  static const int mode_env = getenv("B200_SMALL_MODE") ? atoi(getenv("B200_SMALL_MODE")) : -1;   // 0 free-running, 1 sync/128, 2 sync/256, -1: measured best per class
+  const int mode = mode_env >= 0 ? mode_env : cls == C_GLDM ? 2 : 1;
   if (cls == C_GLSZM || mode == 0) {
     long long need = (total + 127) / 128, cap = (long long)sms * 32;
     const int grid = (int)(need < cap ? need : cap);
