@@ -44,7 +44,10 @@ constexpr int GF_KT = 256;        // |a-b| tables
 #define GF_LOCAL_REORTH 1
 #endif
 #ifndef GF_EXTRA_STEPS
-#define GF_EXTRA_STEPS 3     // float-stored Lanczos vectors lose orthogonality: n-1 steps are not always enough (6e-5 misses seen); +3 steps -> <= 3e-7 over 5e5 windows
+#define GF_EXTRA_STEPS 3     // extra Lanczos steps for tasks that met a small beta (see GF_SMALL_BETA)
+#endif
+#ifndef GF_SMALL_BETA
+#define GF_SMALL_BETA 0.003   // 1e-3 already reproduces the always-extend accuracy (<= 3e-7 over 5e5 windows); 1e-4 does not
 #endif
 #ifndef GF_BREAKDOWN
 #define GF_BREAKDOWN 1e-10
@@ -167,7 +170,8 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const GlcmFastTable
     double beta = 0;
     int m = 0;
     e[0] = 0;
-    const int jmax = n > 4 ? n - 2 + GF_EXTRA_STEPS : n - 2;
+    int jmax = n - 2;
+    bool extended = false;
     for (int j = 0; j <= jmax; j++) {
       for (int i = 0; i < n; i++) z[i] = 0;
       for (int t = 0; t < ne; t++) {
@@ -192,7 +196,11 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const GlcmFastTable
 #endif
       d[m] = alpha; m++;
       nb = sqrt(nb);
-      if (nb < GF_BREAKDOWN || j == jmax) break;       // invariant subspace reached / basis complete
+      if (nb < GF_BREAKDOWN) break;
+      // a small beta amplifies the rounding of the float-stored vectors (orthogonality is lost and
+      // n-1 steps no longer span the space): such tasks run GF_EXTRA_STEPS more steps
+      if (j >= jmax) break;
+      if (nb < GF_SMALL_BETA && !extended && n > 4) { extended = true; jmax += GF_EXTRA_STEPS; }       // invariant subspace reached / basis complete
       e[m] = nb; beta = nb;
       const double inb = 1.0 / nb;
       for (int i = 0; i < n; i++) { q0[i] = q1[i]; q1[i] = z[i] * inb; }
