@@ -40,6 +40,9 @@ constexpr int GF_KT = 256;        // |a-b| tables
 #ifndef RB_LZ_T
 #define RB_LZ_T float
 #endif
+#ifndef RB_TD_T
+#define RB_TD_T float     // storage of the Lanczos tridiagonal (eigenvalue error <= 1e-7)
+#endif
 #ifndef GF_LOCAL_REORTH
 #define GF_LOCAL_REORTH 1
 #endif
@@ -119,7 +122,25 @@ inline void glcm_fast_build_tables(GlcmFastTables& T, int Ng) {
 // known top eigenvector; the extreme eigenvalues of the small tridiagonal are then located by
 // Sturm bisection.  Rebuilds everything from the voxel's 27 window levels (w, stride ws) alone, so
 // any thread can execute any voxel's task.
-RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const GlcmFastTables& T, int s) {
+// the part of the tables the eigen-solver needs (1.1 KB; the solve kernel keeps only this in shared
+// memory so that the L1 carve-out goes to the per-thread Lanczos state)
+struct GlcmSolveTables {
+  uint8_t np[GF_NA];
+  uint8_t pA[GF_NA][18], pB[GF_NA][18];
+  double lz0[19], lz1[19];
+  double rsq[GF_LOGT];
+};
+RB_HD void glcm_solve_tables_from(const GlcmFastTables& T, GlcmSolveTables& S) {
+  for (int a = 0; a < GF_NA; a++) {
+    S.np[a] = T.np[a];
+    for (int t = 0; t < 18; t++) { S.pA[a][t] = T.pA[a][t]; S.pB[a][t] = T.pB[a][t]; }
+  }
+  for (int i = 0; i < 19; i++) { S.lz0[i] = T.lz0[i]; S.lz1[i] = T.lz1[i]; }
+  for (int i = 0; i < GF_LOGT; i++) S.rsq[i] = T.rsq[i];
+}
+
+template <class TT>
+RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const TT& T, int s) {
   const int np = T.np[s];
   const uint8_t* pA = T.pA[s];
   const uint8_t* pB = T.pB[s];
@@ -141,6 +162,26 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const GlcmFastTable
     v1[i] += 1.0; v1[j] += 1.0;
   }
   if (n < 2) return 0.0;
+  {
+    // bipartite (2-colourable, no self-loop) connected graph: eigenvalue -1 -> |.| = 1
+    bool selfloop = false;
+    for (int t = 0; t < ne; t++) selfloop |= ei[t] == ej[t];
+    if (!selfloop) {
+      uint32_t A = 1u, B = 0;            // colour classes as bit sets of node indices
+      for (int sweep = 0; sweep < n; sweep++) {
+        const uint32_t a0 = A, b0 = B;
+        for (int t = 0; t < ne; t++) {
+          const uint32_t bi = 1u << ei[t], bj = 1u << ej[t];
+          if (A & bi) B |= bj;
+          if (B & bi) A |= bj;
+          if (A & bj) B |= bi;
+          if (B & bj) A |= bi;
+        }
+        if (A == a0 && B == b0) break;
+      }
+      if ((A & B) == 0) return 1.0;
+    }
+  }
   // row sums are small integers (<= 36): 1/sqrt from a table
   double S = 0, tr = 0;
   for (int i = 0; i < n; i++) S += v1[i];
@@ -166,7 +207,7 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const GlcmFastTable
     for (int i = 0; i < n; i++) { q1[i] -= dot * v1[i]; nrm += q1[i] * q1[i]; q0[i] = 0; }
     nrm = 1.0 / sqrt(nrm);
     for (int i = 0; i < n; i++) q1[i] *= nrm;
-    double d[19 + GF_EXTRA_STEPS], e[19 + GF_EXTRA_STEPS];
+    RB_TD_T d[19 + GF_EXTRA_STEPS], e[19 + GF_EXTRA_STEPS];
     double beta = 0;
     int m = 0;
     e[0] = 0;
@@ -196,11 +237,11 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const GlcmFastTable
 #endif
       d[m] = alpha; m++;
       nb = sqrt(nb);
-      if (nb < GF_BREAKDOWN) break;
+      if (nb < GF_BREAKDOWN) break;             // invariant subspace reached
       // a small beta amplifies the rounding of the float-stored vectors (orthogonality is lost and
       // n-1 steps no longer span the space): such tasks run GF_EXTRA_STEPS more steps
       if (j >= jmax) break;
-      if (nb < GF_SMALL_BETA && !extended && n > 4) { extended = true; jmax += GF_EXTRA_STEPS; }       // invariant subspace reached / basis complete
+      if (nb < GF_SMALL_BETA && !extended && n > 4) { extended = true; jmax += GF_EXTRA_STEPS; }
       e[m] = nb; beta = nb;
       const double inb = 1.0 / nb;
       for (int i = 0; i < n; i++) { q0[i] = q1[i]; q1[i] = z[i] * inb; }
@@ -208,7 +249,7 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const GlcmFastTable
     if (m <= 2) {                             // closed forms for 1x1 / 2x2
       double hi2 = d[0], lo2 = d[0];
       if (m == 2) {
-        const double mid = 0.5 * (d[0] + d[1]), hd = 0.5 * (d[0] - d[1]), rad = sqrt(hd * hd + e[1] * e[1]);
+        const double mid = 0.5 * ((double)d[0] + d[1]), hd = 0.5 * ((double)d[0] - d[1]), rad = sqrt(hd * hd + (double)e[1] * e[1]);
         hi2 = mid + rad; lo2 = mid - rad;
       }
       best = fmax(best, fmax(fabs(hi2), fabs(lo2)));
@@ -225,7 +266,7 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const GlcmFastTable
       // Sturm count at x: is any eigenvalue <= -|hi| ?  only then the most negative one matters
       double pm2 = 1.0, pm1 = d[0] - x; int cnt = pm1 <= 0;
       for (int i = 1; i < m && !cnt; i++) {
-        const double e2 = e[i] * e[i];
+        const double e2 = (double)e[i] * (double)e[i];
         const double p = (d[i] - x) * pm1 - e2 * pm2;
         const bool neg_prev = pm1 < 0 || (pm1 == 0 && pm2 > 0);
         const bool neg_cur = p < 0 || (p == 0 && !neg_prev);
@@ -262,7 +303,6 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
   int key1[NP], key2[NP];
   uint32_t valid = 0, EA = 0, EB = 0;
   int n = 0, Ssum = 0, Sab = 0, Sq = 0, Skd = 0;
-  bool selfloop = false;
 #pragma unroll
   for (int t = 0; t < NP; t++) {
     const int a = w[pA[t] * ws], b = w[pB[t] * ws];
@@ -273,7 +313,6 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
     if (ok) {
       valid |= 1u << t; EA |= 1u << pA[t]; EB |= 1u << pB[t];
       n++; Ssum += ks; Sab += a * b; Sq += a * a + b * b; Skd += kd;
-      selfloop |= kd == 0;
     }
   }
   const int orig = T.orig[s];
@@ -313,33 +352,12 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
     }
     if (comp != all) mcc = 1.0;
     else {
-      // connected.  A bipartite level graph (no level paired with itself, no odd cycle) has the
-      // eigenvalue -1 next to +1 -> second largest |eigenvalue| = 1 without a solve.
-      bool bip = !selfloop;
-      if (bip) {
-        uint32_t A = 0, B = 0;
-#pragma unroll
-        for (int t = 0; t < NP; t++) if (!A && (valid >> t & 1u)) { A = eq[pA[t] * es]; B = eq[pB[t] * es]; }
-        for (int sweep = 0; sweep < NP; sweep++) {
-          const uint32_t a0 = A, b0 = B;
-#pragma unroll
-          for (int t = 0; t < NP; t++) {
-            if (!(valid >> t & 1u)) continue;
-            const uint32_t a = eq[pA[t] * es], b = eq[pB[t] * es];
-            if (a & A) B |= b;
-            if (a & B) A |= b;
-            if (b & A) B |= a;
-            if (b & B) A |= a;
-          }
-          if (A == a0 && B == b0) break;
-        }
-        bip = (A & B) == 0;
-      }
-      if (bip) mcc = 1.0;
-      else {                                      // eigen-solve queued (phase B)
-        mcc = 0.0; acc.tasks |= 1u << s;
-        acc.tcls |= (unsigned long long)glcm_task_class(nlev) << (3 * s);
-      }
+      // connected: queued for phase B.  (A bipartite level graph -- no level paired with itself, no
+      // odd cycle -- has the eigenvalue -1 next to +1, i.e. MCC = 1 without a solve; that test is
+      // done by the solver thread on its compact edge list: here it would be paid by the whole
+      // warp whenever any lane needs it, ncu: 18 % of this kernel's instructions.)
+      mcc = 0.0; acc.tasks |= 1u << s;
+      acc.tcls |= (unsigned long long)glcm_task_class(nlev) << (3 * s);
     }
   }
   if (NP == 18) { RB_SORTNET_18(key1); RB_SORTNET_18(key2); }

@@ -168,7 +168,8 @@ static RB_HDN void sym_tridiagonalize(double* A, int n, int ld, double* d, doubl
 
 // k-th smallest eigenvalue (k = 0..n-1) of the symmetric tridiagonal (d, e) inside [lo, hi],
 // by bisection on the number of sign changes of the division-free Sturm sequence.
-static RB_HDN double tridiag_kth_eigenvalue(const double* d, const double* e, int n, int k, double lo, double hi,
+template <typename TD>
+static RB_HDN double tridiag_kth_eigenvalue(const TD* d, const TD* e, int n, int k, double lo, double hi,
                                             int iters) {
   for (int it = 0; it < iters; it++) {
     const double x = 0.5 * (lo + hi);
@@ -176,7 +177,7 @@ static RB_HDN double tridiag_kth_eigenvalue(const double* d, const double* e, in
     double pm2 = 1.0, pm1 = d[0] - x;
     int cnt = pm1 <= 0;                      // a zero counts as an eigenvalue <= x
     for (int i = 1; i < n; i++) {
-      const double e2 = e[i] * e[i];
+      const double e2 = (double)e[i] * (double)e[i];
       if (e2 == 0) {                         // decoupled block: restart the sequence
         pm2 = 1.0; pm1 = d[i] - x;
         cnt += pm1 <= 0;
@@ -201,7 +202,8 @@ static RB_HDN double tridiag_kth_eigenvalue(const double* d, const double* e, in
 // spectrum at a Gershgorin bound: for a polynomial with only real roots it converges monotonically
 // and cubically to the nearest (= extreme) root.  p, p', p'' come from the three-term recurrence.
 // Falls back to Sturm bisection if it has not converged after 40 steps.
-static RB_HDN double tridiag_extreme_eigenvalue(const double* d, const double* e, int n, bool top) {
+template <typename TD>
+static RB_HDN double tridiag_extreme_eigenvalue(const TD* d, const TD* e, int n, bool top) {
   double lo = d[0], hi = d[0];
   for (int i = 0; i < n; i++) {
     const double r = (i > 0 ? fabs(e[i]) : 0.0) + (i + 1 < n ? fabs(e[i + 1]) : 0.0);
@@ -212,7 +214,7 @@ static RB_HDN double tridiag_extreme_eigenvalue(const double* d, const double* e
   for (int it = 0; it < 40; it++) {
     double p0 = 1.0, p1 = d[0] - x, q0 = 0.0, q1 = -1.0, r0 = 0.0, r1 = 0.0;   // p, p', p''
     for (int i = 1; i < n; i++) {
-      const double a = d[i] - x, b = e[i] * e[i];
+      const double a = d[i] - x, b = (double)e[i] * (double)e[i];
       const double p2 = a * p1 - b * p0;
       const double q2 = a * q1 - p1 - b * q0;
       const double r2 = a * r1 - 2.0 * q1 - b * r0;

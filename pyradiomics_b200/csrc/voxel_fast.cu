@@ -109,12 +109,8 @@ __global__ void __launch_bounds__(128)
 glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ VoxParams P,
                        const GlcmFastTables* __restrict__ Tg, const GlcmTask* __restrict__ queue,
                        const unsigned* __restrict__ qcount, double* __restrict__ res) {
-  __shared__ GlcmFastTables T;
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(Tg);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
-    for (int i = threadIdx.x; i < (int)(sizeof(GlcmFastTables) / 4); i += blockDim.x) dst[i] = src[i];
-  }
+  __shared__ GlcmSolveTables T;
+  if (threadIdx.x == 0) glcm_solve_tables_from(*Tg, T);
   __syncthreads();
   const unsigned n = *qcount;
   // Tiles of 8 x 128 consecutive tasks are counting-sorted by size class in shared memory, so the
