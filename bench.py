@@ -232,7 +232,7 @@ def run_b200(args):
                 e0.record()
             voxel.voxel_features(c, buf, settings, z0=r, z1=r + nz, out=outs[c], out_z0=r, alive=alive)
             # GLCM = (features, eigen-solve, finish) kernels per plane chunk of the task queue
-            launches += 3 * glcm_chunks if c == "glcm" else 1
+            launches += 5 * glcm_chunks if c == "glcm" else 1   # per plane chunk: phase A, 3 eigen-solve kernels, finish
             if record:
                 e1.record()
                 ev[c].append((e0, e1))

@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200radiomics.so")
+# B200_RADIOMICS_LIB: developer override to A/B a differently-compiled build of the same library
+LIB_PATH = os.environ.get("B200_RADIOMICS_LIB") or os.path.join(HERE, "libb200radiomics.so")
 
 RB_OK, RB_ERR_CUDA, RB_ERR_LEVEL_RANGE, RB_ERR_ARG, RB_ERR_NOMEM, RB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 CLASSES = ("glcm", "glrlm", "glszm", "gldm", "ngtdm")

@@ -28,6 +28,16 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """developer tool: the same library compiled with extra -D flags -> pyradiomics_b200/variants/lib<name>.so
+    (load it with B200_RADIOMICS_LIB=<path>); used to A/B kernel variants inside one GPU session."""
+    out = os.path.join(HERE, "variants", f"lib{name}.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    subprocess.check_call([nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out, *sources(), "-lcuda"], cwd=CSRC)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
@@ -44,4 +54,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 if __name__ == "__main__":
     import sys
 
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:      # python -m pyradiomics_b200.build --variant NAME DEF1=V DEF2=V ...
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

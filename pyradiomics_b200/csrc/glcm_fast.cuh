@@ -43,6 +43,12 @@ constexpr int GF_KT = 256;        // |a-b| tables
 #ifndef RB_TD_T
 #define RB_TD_T float     // storage of the Lanczos tridiagonal (eigenvalue error <= 1e-7)
 #endif
+#ifndef GF_DENSE_SMALL
+#define GF_DENSE_SMALL 1
+#endif
+#ifndef GF_DENSE_MAX_CLS
+#define GF_DENSE_MAX_CLS 10     // n <= 12 solved densely in registers
+#endif
 #ifndef GF_LOCAL_REORTH
 #define GF_LOCAL_REORTH 1
 #endif
@@ -129,11 +135,19 @@ struct GlcmSolveTables {
   uint8_t pA[GF_NA][18], pB[GF_NA][18];
   double lz0[19], lz1[19];
   double rsq[GF_LOGT];
+  // pairs of an angle as bit sets over the 27 window positions: every pair is (p, p + dshift) for a
+  // position p in lo_mask
+  uint32_t lo_mask[GF_NA];
+  uint8_t dshift[GF_NA];
 };
 RB_HD void glcm_solve_tables_from(const GlcmFastTables& T, GlcmSolveTables& S) {
   for (int a = 0; a < GF_NA; a++) {
     S.np[a] = T.np[a];
     for (int t = 0; t < 18; t++) { S.pA[a][t] = T.pA[a][t]; S.pB[a][t] = T.pB[a][t]; }
+    uint32_t lo = 0;
+    for (int t = 0; t < T.np[a]; t++) lo |= 1u << (T.pA[a][t] < T.pB[a][t] ? T.pA[a][t] : T.pB[a][t]);
+    S.lo_mask[a] = lo;
+    S.dshift[a] = (uint8_t)(T.pA[a][0] < T.pB[a][0] ? T.pB[a][0] - T.pA[a][0] : T.pA[a][0] - T.pB[a][0]);
   }
   for (int i = 0; i < 19; i++) { S.lz0[i] = T.lz0[i]; S.lz1[i] = T.lz1[i]; }
   for (int i = 0; i < GF_LOGT; i++) S.rsq[i] = T.rsq[i];
@@ -256,39 +270,227 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const TT& T, int s)
       if (m == n - 1) break;
       continue;
     }
-    // largest eigenvalue of the deflated tridiagonal, then the most negative one only if some
-    // eigenvalue lies below -|hi| (one extra Sturm evaluation decides)
-    // (the Lanczos betas are > 1e-10, so T is unreduced: simple eigenvalues, Laguerre is safe)
-    const double hi = tridiag_extreme_eigenvalue(d, e, m, true);
-    double lo = 0;
-    {
-      const double x = -fabs(hi) - 1e-7;
-      // Sturm count at x: is any eigenvalue <= -|hi| ?  only then the most negative one matters
-      double pm2 = 1.0, pm1 = d[0] - x; int cnt = pm1 <= 0;
-      for (int i = 1; i < m && !cnt; i++) {
-        const double e2 = (double)e[i] * (double)e[i];
-        const double p = (d[i] - x) * pm1 - e2 * pm2;
-        const bool neg_prev = pm1 < 0 || (pm1 == 0 && pm2 > 0);
-        const bool neg_cur = p < 0 || (p == 0 && !neg_prev);
-        cnt += neg_cur != neg_prev;
-        pm2 = pm1; pm1 = p;
-      }
-      if (cnt) lo = tridiag_extreme_eigenvalue(d, e, m, false);
-    }
+    // both extreme eigenvalues of the deflated tridiagonal in one Laguerre loop (the Lanczos betas
+    // are > 1e-10, so T is unreduced: simple eigenvalues)
+    double hi, lo;
+    tridiag_extreme_pair(d, e, m, &hi, &lo);
     best = fmax(best, fmax(fabs(hi), fabs(lo)));
     if (m == n - 1) break;
   }
   return best;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small level graphs (n <= N <= 8, the bulk of the eigen-tasks of smooth images): dense solve held
+// entirely in registers.  Level classes are 27-bit position masks, the co-occurrence counts are
+// popcounts of shifted masks, the normalised matrix is deflated by its known top eigenpair
+// (1, sqrt(R/S)), tridiagonalised by fully unrolled Householder reflections, and the two extreme
+// eigenvalues of the tridiagonal are located by Laguerre's iteration.  No local memory, no
+// start-vector or orthogonality questions (a bipartite graph simply yields the eigenvalue -1).
+#ifdef __CUDA_ARCH__
+#define RB_VCMPEQ4_LSB(a, b) (__vcmpeq4((a), (b)) & 0x01010101u)
+#else
+static inline uint32_t rb_vcmpeq4_lsb(uint32_t a, uint32_t b) {
+  const uint32_t x = a ^ b;                                  // zero byte <=> equal
+  const uint32_t t = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu;
+  return (~t) >> 7;                                         // 0x01 per equal byte
+}
+#define RB_VCMPEQ4_LSB(a, b) rb_vcmpeq4_lsb((a), (b))
+#endif
+
+// W7: the 27 window levels packed 4 per word (byte p & 3 of word p >> 2; the 28th byte is 0).
+RB_HD void glcm_pack_window(const uint8_t* w, int ws, uint32_t* W7) {
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) if (4 * k + b < 27) v |= (uint32_t)w[(4 * k + b) * ws] << (8 * b);
+    W7[k] = v;
+  }
+}
+// bit p set <=> window position p holds `lev`
+RB_HD uint32_t glcm_eq_positions(const uint32_t* W7, uint32_t lev) {
+  const uint32_t rep = lev * 0x01010101u;
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 7; k++) m |= ((RB_VCMPEQ4_LSB(W7[k], rep) * 0x01020408u) >> 24) << (4 * k);
+  return m & 0x7FFFFFFu;
+}
+
+// both extreme eigenvalues of the symmetric tridiagonal (d[0..N-1], e[1..N-1]) held in registers:
+// two Laguerre iterations from outside the spectrum (monotone; cubic for a simple root, linear for
+// a repeated one) advanced in one loop, Sturm bisection for an end that has not settled.
+template <int N>
+RB_HD double tridiag_bisect_static(const double* d, const double* e, double lo, double hi, int k) {
+  for (int it = 0; it < 36; it++) {
+    const double xm = 0.5 * (lo + hi);
+    double pm2 = 1.0, pm1 = d[0] - xm;
+    int cnt = pm1 <= 0;
+#pragma unroll
+    for (int i = 1; i < N; i++) {
+      const double e2 = e[i] * e[i];
+      if (e2 == 0) { pm2 = 1.0; pm1 = d[i] - xm; cnt += pm1 <= 0; continue; }
+      const double p = (d[i] - xm) * pm1 - e2 * pm2;
+      const bool neg_prev = pm1 < 0 || (pm1 == 0 && pm2 > 0);
+      const bool neg_cur = p < 0 || (p == 0 && !neg_prev);
+      cnt += neg_cur != neg_prev;
+      pm2 = pm1; pm1 = p;
+    }
+    if (cnt > k) hi = xm; else lo = xm;
+  }
+  return 0.5 * (lo + hi);
+}
+template <int N>
+RB_HD void tridiag_extreme_pair_static(const double* d, const double* e, double* hi_out, double* lo_out) {
+  double lo = d[0], hi = d[0];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const double r = (i > 0 ? fabs(e[i]) : 0.0) + (i + 1 < N ? fabs(e[i + 1]) : 0.0);
+    lo = fmin(lo, d[i] - r); hi = fmax(hi, d[i] + r);
+  }
+  double x[2] = {hi + 1e-9, lo - 1e-9};
+  bool done[2] = {false, false};
+  for (int it = 0; it < 24 && !(done[0] && done[1]); it++) {
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      double p0 = 1.0, p1 = d[0] - x[c], q0 = 0.0, q1 = -1.0, r0 = 0.0, r1 = 0.0;   // p, p', p''
+#pragma unroll
+      for (int i = 1; i < N; i++) {
+        const double a = d[i] - x[c], b = e[i] * e[i];
+        const double p2 = a * p1 - b * p0;
+        const double q2 = a * q1 - p1 - b * q0;
+        const double r2 = a * r1 - 2.0 * q1 - b * r0;
+        p0 = p1; p1 = p2; q0 = q1; q1 = q2; r0 = r1; r1 = r2;
+      }
+      if (done[c]) continue;
+      if (p1 == 0) { done[c] = true; continue; }
+      const double G = q1 / p1, H = G * G - r1 / p1;
+      const double disc = (double)(N - 1) * ((double)N * H - G * G);
+      const double sq = sqrt(disc > 0 ? disc : 0.0);
+      const double den = fabs(G + sq) > fabs(G - sq) ? G + sq : G - sq;
+      if (den == 0 || den != den) continue;            // stalls: left to the bisection below
+      const double step = (double)N / den;
+      x[c] -= step;
+      if (fabs(step) < 1e-10) done[c] = true;
+    }
+  }
+  *hi_out = done[0] ? x[0] : tridiag_bisect_static<N>(d, e, lo - 1e-9, hi + 1e-9, N - 1);
+  *lo_out = done[1] ? x[1] : tridiag_bisect_static<N>(d, e, lo - 1e-9, hi + 1e-9, 0);
+}
+
+// second largest |eigenvalue| of the normalised co-occurrence matrix of angle slot s whose level
+// graph has at most N nodes.  *ok = false (nothing computed) if it has more.
+template <int N, class TT>
+RB_HD double glcm_small_solve(const uint8_t* w, int ws, const uint32_t* W7, const TT& T, int s, bool* ok) {
+  const int dsh = T.dshift[s];
+  const uint32_t NZ = ~glcm_eq_positions(W7, 0u) & 0x7FFFFFFu;
+  const uint32_t VL = NZ & (NZ >> dsh) & T.lo_mask[s];        // valid pairs, by their lower position
+  uint32_t U = VL | (VL << dsh);                               // positions of all pair ends
+  uint32_t El[N], Eh[N];
+  int R[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint32_t E = 0;
+    if (U) { E = glcm_eq_positions(W7, w[RB_CTZ(U) * ws]); U &= ~E; }
+    El[i] = E & VL;                 // pairs whose lower end is in class i
+    Eh[i] = (E >> dsh) & VL;        // pairs whose upper end is in class i
+    R[i] = RB_POPC(El[i]) + RB_POPC(Eh[i]);
+  }
+  if (U) { *ok = false; return 0.0; }
+  *ok = true;
+  const double invS = 1.0 / (2.0 * RB_POPC(VL));
+  double v1[N], rs[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) { rs[i] = T.rsq[R[i]]; v1[i] = sqrt(R[i] * invS); }
+  // deflated matrix A = M - v1 v1^T (lower triangle used)
+  double a[N][N];
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j <= i; j++) {
+      const int c = (i == j) ? 2 * RB_POPC(El[i] & Eh[i]) : RB_POPC(El[i] & Eh[j]) + RB_POPC(El[j] & Eh[i]);
+      a[i][j] = c * rs[i] * rs[j] - v1[i] * v1[j];
+    }
+  // Householder tridiagonalisation, column by column (k = column being reduced)
+  double d[N], e[N];
+  e[0] = 0;
+#pragma unroll
+  for (int k = 0; k + 2 < N; k++) {
+    double sigma = 0;
+#pragma unroll
+    for (int i = k + 2; i < N; i++) sigma += a[i][k] * a[i][k];
+    const double x0 = a[k + 1][k];
+    d[k] = a[k][k];
+    if (sigma < 1e-30) { e[k + 1] = x0; continue; }      // column already tridiagonal
+    const double nrm = sqrt(x0 * x0 + sigma);
+    const double alpha = x0 > 0 ? -nrm : nrm;
+    double v[N], pv[N];
+    v[k + 1] = x0 - alpha;
+#pragma unroll
+    for (int i = k + 2; i < N; i++) v[i] = a[i][k];
+    const double beta = -1.0 / (alpha * v[k + 1]);            // 2 / v^T v
+    double K = 0;
+#pragma unroll
+    for (int i = k + 1; i < N; i++) {
+      double acc = 0;
+#pragma unroll
+      for (int j = k + 1; j < N; j++) acc += (j <= i ? a[i][j] : a[j][i]) * v[j];
+      pv[i] = beta * acc;
+      K += v[i] * pv[i];
+    }
+    K *= 0.5 * beta;
+#pragma unroll
+    for (int i = k + 1; i < N; i++) pv[i] -= K * v[i];
+#pragma unroll
+    for (int i = k + 1; i < N; i++)
+#pragma unroll
+      for (int j = k + 1; j <= i; j++) a[i][j] -= v[i] * pv[j] + pv[i] * v[j];
+    e[k + 1] = alpha;
+  }
+  d[N - 2] = a[N - 2][N - 2]; e[N - 1] = a[N - 1][N - 2]; d[N - 1] = a[N - 1][N - 1];
+  double hi, lo;
+  tridiag_extreme_pair_static<N>(d, e, &hi, &lo);
+  return fmax(fabs(hi), fabs(lo));
+}
+
+// eigen-task entry point.  cls = n - 2 (glcm_task_class).  KIND selects the size range one solve kernel
+// handles: 0: n <= 8 and 1: n <= 12 (dense register solves), 2: larger graphs (sparse Lanczos),
+// -1: any (host emulation).
+template <int KIND, class TT>
+RB_HD double glcm_fast_solve(const uint8_t* w, int ws, const TT& T, int s, int cls) {
+#if GF_DENSE_SMALL
+  if ((KIND == 0 || KIND == 1 || KIND == -1) && cls <= GF_DENSE_MAX_CLS) {
+    uint32_t W7[7];
+    glcm_pack_window(w, ws, W7);
+    bool ok = false;
+    double r = 0;
+    if (KIND != 1 && cls <= 6) {
+      if (cls <= 2) r = glcm_small_solve<4>(w, ws, W7, T, s, &ok);
+      else if (cls <= 4) r = glcm_small_solve<6>(w, ws, W7, T, s, &ok);
+      else r = glcm_small_solve<8>(w, ws, W7, T, s, &ok);
+    } else if (KIND != 0) {
+      if (cls <= 8) r = glcm_small_solve<10>(w, ws, W7, T, s, &ok);
+      else r = glcm_small_solve<12>(w, ws, W7, T, s, &ok);
+    }
+    if (ok) return r;
+    if (KIND != -1) return NAN;        // cannot happen: cls is the exact node count
+  }
+#endif
+  if (KIND == 0 || KIND == 1) return NAN;
+  return glcm_fast_solve_task(w, ws, T, s);
+}
+
 // size class of an eigen-task (number of level nodes) -- tasks of one class share a warp
-RB_HD int glcm_task_class(int n) { return n <= 3 ? 0 : n <= 4 ? 1 : n <= 6 ? 2 : n <= 8 ? 3 : n <= 11 ? 4 : n <= 14 ? 5 : n <= 16 ? 6 : 7; }
+// (16 keys: n - 2, clamped; ncu showed 11 of 32 lanes active with 8 coarser classes because the loop
+// lengths of the sparse solver follow n)
+constexpr int GF_NCLS = 16, GF_CLS_BITS = 4;
+RB_HD int glcm_task_class(int n) { return n <= 2 ? 0 : n >= 17 ? 15 : n - 2; }
 
 struct GlcmAcc {
   double sum[GLCM_NF];
   int n_ok, n_imc2;
   uint32_t tasks;      // bit s set: angle slot s needs an MCC eigen-solve (added to sum[G_MCC] later)
-  unsigned long long tcls;   // 3 bits per slot: size class of the task (see glcm_task_class)
+  unsigned long long tcls;   // GF_CLS_BITS per slot: size class of the task (see glcm_task_class)
   bool ja_nan;
 };
 
@@ -357,7 +559,7 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
       // done by the solver thread on its compact edge list: here it would be paid by the whole
       // warp whenever any lane needs it, ncu: 18 % of this kernel's instructions.)
       mcc = 0.0; acc.tasks |= 1u << s;
-      acc.tcls |= (unsigned long long)glcm_task_class(nlev) << (3 * s);
+      acc.tcls |= (unsigned long long)glcm_task_class(nlev) << (GF_CLS_BITS * s);
     }
   }
   if (NP == 18) { RB_SORTNET_18(key1); RB_SORTNET_18(key2); }
@@ -480,9 +682,12 @@ RB_HD double glcm_fast_finish_mcc(double partial_mean, int n_ok, uint32_t tasks,
 RB_HD void glcm_fast_voxel(const uint8_t* w, int ws, uint32_t* eq, int es, const GlcmFastTables& T,
                            const VoxParams& P, double* out) {
   int n_ok = 0;
-  const uint32_t tasks = glcm_fast_voxel_phaseA(w, ws, eq, es, T, P, out, &n_ok);
+  unsigned long long tcls = 0;
+  const uint32_t tasks = glcm_fast_voxel_phaseA(w, ws, eq, es, T, P, out, &n_ok, &tcls);
   double solved[GF_NA];
-  for (int s = 0; s < GF_NA; s++) solved[s] = (tasks >> s & 1u) ? glcm_fast_solve_task(w, ws, T, s) : 0.0;
+  GlcmSolveTables ST;
+  glcm_solve_tables_from(T, ST);
+  for (int s = 0; s < GF_NA; s++) solved[s] = (tasks >> s & 1u) ? glcm_fast_solve<-1>(w, ws, ST, s, (int)(tcls >> (GF_CLS_BITS * s) & (GF_NCLS - 1))) : 0.0;
   out[G_MCC] = glcm_fast_finish_mcc(out[G_MCC], n_ok, tasks, solved, 1);
 }
 

@@ -233,6 +233,66 @@ static RB_HDN double tridiag_extreme_eigenvalue(const TD* d, const TD* e, int n,
   return tridiag_kth_eigenvalue(d, e, n, top ? n - 1 : 0, lo - 1e-9, hi + 1e-9, 40);
 }
 
+// Both extreme eigenvalues of an unreduced symmetric tridiagonal in one Laguerre loop (one pass over
+// d, e per iteration serves both ends; lanes of a warp do not serialise "top" and "bottom" calls).
+template <typename TD>
+static RB_HDN void tridiag_extreme_pair(const TD* d, const TD* e, int n, double* hi_out, double* lo_out) {
+  double lo = d[0], hi = d[0];
+  for (int i = 0; i < n; i++) {
+    const double r = (i > 0 ? fabs((double)e[i]) : 0.0) + (i + 1 < n ? fabs((double)e[i + 1]) : 0.0);
+    lo = fmin(lo, d[i] - r); hi = fmax(hi, d[i] + r);
+  }
+  if (n == 1) { *hi_out = d[0]; *lo_out = d[0]; return; }
+  double xh = hi + 1e-9, xl = lo - 1e-9;
+  bool dh = false, dl = false;
+  for (int it = 0; it < 40 && !(dh && dl); it++) {
+    const double d0 = d[0];
+    double hp0 = 1.0, hp1 = d0 - xh, hq0 = 0.0, hq1 = -1.0, hr0 = 0.0, hr1 = 0.0;
+    double lp0 = 1.0, lp1 = d0 - xl, lq0 = 0.0, lq1 = -1.0, lr0 = 0.0, lr1 = 0.0;
+    for (int i = 1; i < n; i++) {
+      const double di = d[i], b = (double)e[i] * (double)e[i];
+      {
+        const double a = di - xh;
+        const double p2 = a * hp1 - b * hp0, q2 = a * hq1 - hp1 - b * hq0, r2 = a * hr1 - 2.0 * hq1 - b * hr0;
+        hp0 = hp1; hp1 = p2; hq0 = hq1; hq1 = q2; hr0 = hr1; hr1 = r2;
+      }
+      {
+        const double a = di - xl;
+        const double p2 = a * lp1 - b * lp0, q2 = a * lq1 - lp1 - b * lq0, r2 = a * lr1 - 2.0 * lq1 - b * lr0;
+        lp0 = lp1; lp1 = p2; lq0 = lq1; lq1 = q2; lr0 = lr1; lr1 = r2;
+      }
+    }
+    if (!dh) {
+      if (hp1 == 0) dh = true;
+      else {
+        const double G = hq1 / hp1, H = G * G - hr1 / hp1;
+        const double disc = (double)(n - 1) * ((double)n * H - G * G);
+        const double sq = sqrt(disc > 0 ? disc : 0.0);
+        const double den = fabs(G + sq) > fabs(G - sq) ? G + sq : G - sq;
+        if (den == 0 || den != den) break;
+        const double step = (double)n / den;
+        xh -= step;
+        if (fabs(step) < 1e-11) dh = true;
+      }
+    }
+    if (!dl) {
+      if (lp1 == 0) dl = true;
+      else {
+        const double G = lq1 / lp1, H = G * G - lr1 / lp1;
+        const double disc = (double)(n - 1) * ((double)n * H - G * G);
+        const double sq = sqrt(disc > 0 ? disc : 0.0);
+        const double den = fabs(G + sq) > fabs(G - sq) ? G + sq : G - sq;
+        if (den == 0 || den != den) break;
+        const double step = (double)n / den;
+        xl -= step;
+        if (fabs(step) < 1e-11) dl = true;
+      }
+    }
+  }
+  *hi_out = dh ? xh : tridiag_kth_eigenvalue(d, e, n, n - 1, lo - 1e-9, hi + 1e-9, 40);
+  *lo_out = dl ? xl : tridiag_kth_eigenvalue(d, e, n, 0, lo - 1e-9, hi + 1e-9, 40);
+}
+
 // Second-largest eigenvalue of a symmetric positive semi-definite matrix with spectrum in [0, 1+]
 // (the generic MCC path: A = M M^T).  n >= 2.
 static RB_HDN double sym_psd_second_largest(double* A, int n, int ld, double* d, double* e) {

@@ -32,7 +32,7 @@ struct GlcmTask {
   uint8_t slot;        // angle slot to solve
   uint8_t n_ok;        // number of non-empty angles of the voxel (the nanmean denominator)
   uint8_t count;       // > 0 on the first task of a voxel: how many consecutive entries belong to it
-  uint8_t cls;         // size class of the task (0..3), used to group similar tasks in a warp
+  uint8_t cls;         // size class of the task (glcm_task_class), groups similar tasks in a warp
   float unused;
 };
 
@@ -97,7 +97,7 @@ glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ ce
       for (uint32_t m = tasks; m; m &= m - 1, q++) {
         GlcmTask e;
         e.vi = vi; e.slot = (uint8_t)(__ffs((int)m) - 1); e.n_ok = (uint8_t)n_ok; e.count = first ? (uint8_t)k : 0;
-        e.cls = (uint8_t)(tcls >> (3 * e.slot) & 7u); e.unused = 0.f;
+        e.cls = (uint8_t)(tcls >> (GF_CLS_BITS * e.slot) & (GF_NCLS - 1)); e.unused = 0.f;
         queue[q] = e;
         first = false;
       }
@@ -105,7 +105,16 @@ glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ ce
   }
 }
 
-__global__ void __launch_bounds__(128)
+// Phase B.  KIND 0: tasks with n <= 8 levels, KIND 1: 9..12 (dense register solves, see
+// glcm_small_solve), KIND 2: larger level graphs (sparse Lanczos with per-thread scratch).  Each is
+// its own kernel because the three want very different register budgets.
+template <int KIND> struct SolveKind;
+template <> struct SolveKind<0> { static constexpr int lo = 0, hi = 6, minb = 4; };
+template <> struct SolveKind<1> { static constexpr int lo = 7, hi = GF_DENSE_MAX_CLS, minb = 2; };
+template <> struct SolveKind<2> { static constexpr int lo = GF_DENSE_MAX_CLS + 1, hi = GF_NCLS - 1, minb = 4; };
+
+template <int KIND>
+__global__ void __launch_bounds__(128, SolveKind<KIND>::minb)
 glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ VoxParams P,
                        const GlcmFastTables* __restrict__ Tg, const GlcmTask* __restrict__ queue,
                        const unsigned* __restrict__ qcount, double* __restrict__ res) {
@@ -114,34 +123,37 @@ glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ 
   __syncthreads();
   const unsigned n = *qcount;
   // Tiles of 8 x 128 consecutive tasks are counting-sorted by size class in shared memory, so the
-  // lanes of a warp run Lanczos recurrences of similar length (ncu: 14 of 32 lanes active before).
+  // lanes of a warp run solves of the same size (ncu: 11-14 of 32 lanes active otherwise).
   constexpr int TILE = 1024;
   __shared__ uint16_t order[TILE];
-  __shared__ int bucket[8];
+  __shared__ int bucket[GF_NCLS];
   const unsigned ntiles = (n + TILE - 1) / TILE;
   for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const unsigned base = tile * TILE;
-    if (threadIdx.x < 8) bucket[threadIdx.x] = 0;
+    if (threadIdx.x < GF_NCLS) bucket[threadIdx.x] = 0;
     __syncthreads();
     uint8_t mycls[TILE / 128];
 #pragma unroll
     for (int j = 0; j < TILE / 128; j++) {
       const unsigned k = base + j * 128 + threadIdx.x;
-      mycls[j] = k < n ? queue[k].cls : 8;
-      if (mycls[j] < 8) atomicAdd(&bucket[mycls[j]], 1);
+      mycls[j] = k < n ? queue[k].cls : GF_NCLS;
+      if (mycls[j] >= SolveKind<KIND>::lo && mycls[j] <= SolveKind<KIND>::hi) atomicAdd(&bucket[mycls[j]], 1);
     }
     __syncthreads();
-    int start[8];
-    start[0] = 0;
+    int start = 0, ntile = 0;            // exclusive prefix of this thread's bucket (threads < GF_NCLS)
 #pragma unroll
-    for (int c = 1; c < 8; c++) start[c] = start[c - 1] + bucket[c - 1];
-    const int ntile = start[7] + bucket[7];
+    for (int c = SolveKind<KIND>::lo; c <= SolveKind<KIND>::hi; c++) {
+      const int b = bucket[c];
+      if (c < (int)threadIdx.x) start += b;
+      ntile += b;
+    }
     __syncthreads();
-    if (threadIdx.x < 8) bucket[threadIdx.x] = start[threadIdx.x];
+    if (threadIdx.x < GF_NCLS) bucket[threadIdx.x] = start;
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < TILE / 128; j++)
-      if (mycls[j] < 8) order[atomicAdd(&bucket[mycls[j]], 1)] = (uint16_t)(j * 128 + threadIdx.x);
+      if (mycls[j] >= SolveKind<KIND>::lo && mycls[j] <= SolveKind<KIND>::hi)
+        order[atomicAdd(&bucket[mycls[j]], 1)] = (uint16_t)(j * 128 + threadIdx.x);
     __syncthreads();
     for (int i = threadIdx.x; i < ntile; i += 128) {
       const unsigned k = base + order[i];
@@ -159,7 +171,7 @@ glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ 
             const bool in = zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
             w[p] = in ? lev[e.vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : (uint8_t)0;
           }
-      res[k] = glcm_fast_solve_task(w, 1, T, e.slot);
+      res[k] = glcm_fast_solve<KIND>(w, 1, T, e.slot, e.cls);
     }
     __syncthreads();
   }
@@ -266,7 +278,9 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
     }
     RB_LAUNCH_CHECK();
     static const int solve_bps = getenv("B200_GLCM_SOLVE_BPS") ? atoi(getenv("B200_GLCM_SOLVE_BPS")) : 8;
-    glcm_fast_solve_kernel<<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
+    glcm_fast_solve_kernel<0><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
+    glcm_fast_solve_kernel<1><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
+    glcm_fast_solve_kernel<2><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
     RB_LAUNCH_CHECK();
     glcm_fast_finish_kernel<<<sms * 8, 256, 0, st>>>(P, Q->q, Q->count, Q->res, out + (long long)G_MCC * fstride, out_z0);
     RB_LAUNCH_CHECK();

@@ -73,12 +73,35 @@ extern "C" int emul_glcm_fast(const uint16_t* lev, int Z, int Y, int X, const Vo
 extern "C" double emul_glcm_solve_window(const uint8_t* w, int slot, int Ng) {
   GlcmFastTables* T = new GlcmFastTables;
   glcm_fast_build_tables(*T, Ng);
-  double r = glcm_fast_solve_task(w, 1, *T, slot);
+  GlcmSolveTables ST;
+  glcm_solve_tables_from(*T, ST);
+  double r = glcm_fast_solve_task(w, 1, ST, slot);
   delete T;
   return r;
 }
 
 #include "../../pyradiomics_b200/csrc/glrlm_fast.cuh"
+// same task through the dispatcher (dense register solve for <= 8 levels); cls < 0: derive it
+extern "C" double emul_glcm_solve_window_cls(const uint8_t* w, int slot, int Ng, int cls) {
+  GlcmFastTables* T = new GlcmFastTables;
+  glcm_fast_build_tables(*T, Ng);
+  GlcmSolveTables ST;
+  glcm_solve_tables_from(*T, ST);
+  if (cls < 0) {
+    bool seen[256] = {false}; int n = 0;
+    for (int t = 0; t < ST.np[slot]; t++) {
+      const uint8_t a = w[ST.pA[slot][t]], b = w[ST.pB[slot][t]];
+      if (!a || !b) continue;
+      if (!seen[a]) { seen[a] = true; n++; }
+      if (!seen[b]) { seen[b] = true; n++; }
+    }
+    cls = glcm_task_class(n);
+  }
+  double r = glcm_fast_solve<-1>(w, 1, ST, slot, cls);
+  delete T;
+  return r;
+}
+
 // GLRLM fast path (r=1, 13 angles, unweighted, 8-bit levels) on the host
 extern "C" int emul_glrlm_fast(const uint16_t* lev, int Z, int Y, int X, const VoxSettings* s, double* out) {
   VoxParams P;
