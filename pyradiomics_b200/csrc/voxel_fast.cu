@@ -108,10 +108,19 @@ glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ ce
 // Phase B.  KIND 0: tasks with n <= 8 levels, KIND 1: 9..12 (dense register solves, see
 // glcm_small_solve), KIND 2: larger level graphs (sparse Lanczos with per-thread scratch).  Each is
 // its own kernel because the three want very different register budgets.
+#ifndef GF_SOLVE_MINB_S
+#define GF_SOLVE_MINB_S 4
+#endif
+#ifndef GF_SOLVE_MINB_L
+#define GF_SOLVE_MINB_L 8
+#endif
+#ifndef GF_SOLVE_TILE
+#define GF_SOLVE_TILE 2048
+#endif
 template <int KIND> struct SolveKind;
-template <> struct SolveKind<0> { static constexpr int lo = 0, hi = 6, minb = 4; };
+template <> struct SolveKind<0> { static constexpr int lo = 0, hi = 6, minb = GF_SOLVE_MINB_S; };
 template <> struct SolveKind<1> { static constexpr int lo = 7, hi = GF_DENSE_MAX_CLS, minb = 2; };
-template <> struct SolveKind<2> { static constexpr int lo = GF_DENSE_MAX_CLS + 1, hi = GF_NCLS - 1, minb = 4; };
+template <> struct SolveKind<2> { static constexpr int lo = GF_DENSE_MAX_CLS + 1, hi = GF_NCLS - 1, minb = GF_SOLVE_MINB_L; };
 
 template <int KIND>
 __global__ void __launch_bounds__(128, SolveKind<KIND>::minb)
@@ -124,7 +133,7 @@ glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ 
   const unsigned n = *qcount;
   // Tiles of 8 x 128 consecutive tasks are counting-sorted by size class in shared memory, so the
   // lanes of a warp run solves of the same size (ncu: 11-14 of 32 lanes active otherwise).
-  constexpr int TILE = 1024;
+  constexpr int TILE = GF_SOLVE_TILE;
   __shared__ uint16_t order[TILE];
   __shared__ int bucket[GF_NCLS];
   const unsigned ntiles = (n + TILE - 1) / TILE;
