@@ -174,6 +174,22 @@ int rb_recursive_gaussian_axis_dev(const void *in_dev, int in_is_f32, int Z, int
                                    const double *coef20, float *out_dev, double *scratch_dev, double scale,
                                    int accumulate, void *stream);
 
+/* ---- segment-mode shape coefficients ------------------------------
+ * rb_calculate_coefficients replaces calculate_coefficients (radiomics/src/cshape.h:1-2, binding
+ *   radiomics/src/_cshape.c:75-113): HOST mask (non-zero = ROI) of `size` = {Z, Y, X} with element
+ *   `strides`, `spacing` = {z, y, x}; marching-cubes surface area and volume of the ROI mesh and the
+ *   four maximum diameters (equal-z "Slice", equal-y "Column", equal-x "Row", 3-D) over its vertices.
+ *   The diameters are bit-identical to the reference's; area / volume differ by summation order only.
+ * rb_shape_coefficients_dev: the same for a contiguous uint8 mask already on the device; out7 (HOST) =
+ *   {area, volume, d_slice, d_column, d_row, d_3D, number of mesh vertices}.  Synchronises `stream`.
+ * rb_shape_moments_dev: exact integer moments {N, z, y, x, zz, zy, zx, yy, yx, xx} of the ROI voxel
+ *   indices (the covariance of shape.py:86-95 is formed from them on the host). */
+int rb_calculate_coefficients(const char *mask, const int *size, const int *strides, const double *spacing,
+                              double *surfaceArea, double *volume, double *diameters);
+int rb_shape_coefficients_dev(const uint8_t *mask_dev, int Z, int Y, int X, const double *spacing_zyx,
+                              double *out7, void *stream);
+int rb_shape_moments_dev(const uint8_t *mask_dev, int Z, int Y, int X, unsigned long long *out10, void *stream);
+
 /* ---- voxel-based first-order feature maps (the next plugin after the five
  *      texture classes; reference radiomics/firstorder.py:40-474).  For every centre voxel of planes
  *      [z0,z1): the 18 first-order features over its kernel window (radii rz,ry,rx per dimension: the

@@ -20,15 +20,18 @@ REF_SRC = "/root/reference/radiomics/src"
 OUT_DIR = os.path.join(HERE, "_ref")
 
 
-def ref_so_path() -> str:
-    return os.path.join(OUT_DIR, "_cmatrices" + sysconfig.get_config_var("EXT_SUFFIX"))
+MODULES = {"_cmatrices": ["_cmatrices.c", "cmatrices.c"], "_cshape": ["_cshape.c", "cshape.c"]}
 
 
-def build(force: bool = False) -> str | None:
+def ref_so_path(name: str = "_cmatrices") -> str:
+    return os.path.join(OUT_DIR, name + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build(force: bool = False, name: str = "_cmatrices") -> str | None:
     """Return the path of the built module, or None when the reference sources are absent
     (GPU box) and no prebuilt file exists."""
-    out = ref_so_path()
-    srcs = [os.path.join(REF_SRC, "_cmatrices.c"), os.path.join(REF_SRC, "cmatrices.c")]
+    out = ref_so_path(name)
+    srcs = [os.path.join(REF_SRC, f) for f in MODULES[name]]
     if not all(os.path.exists(s) for s in srcs):
         return out if os.path.exists(out) else None
     if os.path.exists(out) and not force:
@@ -48,14 +51,14 @@ def build(force: bool = False) -> str | None:
     return out
 
 
-def load():
+def load(name: str = "_cmatrices"):
     """Import the compiled reference module as a standalone module object."""
     import importlib.util
 
-    path = build()
+    path = build(name=name)
     if path is None:
-        raise ImportError("reference _cmatrices not built and /root/reference absent")
-    spec = importlib.util.spec_from_file_location("_cmatrices", path)
+        raise ImportError(f"reference {name} not built and /root/reference absent")
+    spec = importlib.util.spec_from_file_location(name, path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod

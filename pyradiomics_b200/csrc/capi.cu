@@ -58,6 +58,9 @@ int glszm_fill_host(void* handle, int Ng, int max_region, double* out_host);
 void glszm_release(void* handle);
 
 int minmax_launch(const void* img, int dt, const uint8_t* mask, long long n, long long* keys, cudaStream_t st);
+int shape_coefficients_dev(const uint8_t* mask_dev, int Z, int Y, int X, long long sz, long long sy, long long sx,
+                           const double* spacing, double* out7, cudaStream_t st);
+int shape_moments_dev(const uint8_t* mask_dev, int Z, int Y, int X, unsigned long long* out10, cudaStream_t st);
 int digitize_launch(const void* img, int dt, const uint8_t* mask, long long n, const double* edges, int ne, int32_t* out,
                     cudaStream_t st);
 int swt_axis_launch(const double* in, int Z, int Y, int X, int axis, const double* lo, const double* hi, int F,
@@ -265,6 +268,39 @@ int rb_recursive_gaussian_axis_dev(const void* in_dev, int in_is_f32, int Z, int
   if (axis < 0 || axis > 2) return fail(RB_ERR_ARG, "axis must be 0..2");
   return recursive_gauss_launch(in_dev, in_is_f32, Z, Y, X, axis, coef20, out_dev, scratch_dev, scale, accumulate,
                                 (cudaStream_t)stream);
+}
+
+int rb_shape_coefficients_dev(const uint8_t* mask_dev, int Z, int Y, int X, const double* spacing_zyx, double* out7,
+                              void* stream) {
+  if (!mask_dev || !spacing_zyx || !out7 || Z < 1 || Y < 1 || X < 1) return fail(RB_ERR_ARG, "shape: bad arguments");
+  return shape_coefficients_dev(mask_dev, Z, Y, X, (long long)Y * X, X, 1, spacing_zyx, out7, (cudaStream_t)stream);
+}
+int rb_shape_moments_dev(const uint8_t* mask_dev, int Z, int Y, int X, unsigned long long* out10, void* stream) {
+  if (!mask_dev || !out10 || Z < 1 || Y < 1 || X < 1) return fail(RB_ERR_ARG, "shape: bad arguments");
+  return shape_moments_dev(mask_dev, Z, Y, X, out10, (cudaStream_t)stream);
+}
+int rb_calculate_coefficients(const char* mask, const int* size, const int* strides, const double* spacing,
+                              double* surfaceArea, double* volume, double* diameters) {
+  if (!mask || !size || !strides || !spacing || !surfaceArea || !volume || !diameters) return fail(RB_ERR_ARG, "shape: null argument");
+  const int Z = size[0], Y = size[1], X = size[2];
+  if (Z < 1 || Y < 1 || X < 1) return fail(RB_ERR_ARG, "shape: bad size");
+  const size_t n = (size_t)Z * Y * X;
+  std::vector<uint8_t> packed(n);
+  for (int z = 0; z < Z; z++)
+    for (int y = 0; y < Y; y++)
+      for (int x = 0; x < X; x++)
+        packed[((size_t)z * Y + y) * X + x] = mask[(long long)z * strides[0] + (long long)y * strides[1] + (long long)x * strides[2]] != 0;
+  uint8_t* d = nullptr;
+  RB_CUDA(cudaMalloc(&d, n));
+  cudaError_t e = cudaMemcpy(d, packed.data(), n, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d); return fail(RB_ERR_CUDA, "shape: %s", cudaGetErrorString(e)); }
+  double out7[7];
+  const int rc = shape_coefficients_dev(d, Z, Y, X, (long long)Y * X, X, 1, spacing, out7, 0);
+  cudaFree(d);
+  if (rc) return rc;
+  *surfaceArea = out7[0]; *volume = out7[1];
+  for (int q = 0; q < 4; q++) diameters[q] = out7[2 + q];
+  return RB_OK;
 }
 
 int rb_firstorder_num_features(void) { return 18; }

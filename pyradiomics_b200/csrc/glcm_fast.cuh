@@ -43,15 +43,6 @@ constexpr int GF_KT = 256;        // |a-b| tables
 #ifndef RB_TD_T
 #define RB_TD_T float     // storage of the Lanczos tridiagonal (eigenvalue error <= 1e-7)
 #endif
-#ifndef GF_CSR_LANCZOS
-#define GF_CSR_LANCZOS 1
-#endif
-#ifndef GF_SECOND_ROUND
-#define GF_SECOND_ROUND 1
-#endif
-#ifndef GF_SECOND_ROUND_RATIO
-#define GF_SECOND_ROUND_RATIO 0.5     // |z|^2 < ratio |M q|^2: heavy cancellation, orthogonalise once more (Kahan-Parlett "twice is enough")
-#endif
 #ifndef GF_DENSE_SMALL
 #define GF_DENSE_SMALL 1
 #endif
@@ -205,95 +196,6 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const TT& T, int s)
       if ((A & B) == 0) return 1.0;
     }
   }
-#if GF_CSR_LANCZOS
-  // ---- fused formulation: adjacency in CSR form (gather mat-vec, no zeroing / read-modify-write),
-  // the three projection coefficients taken while the product is formed, one correction pass, and
-  // rotating vector buffers with a carried scale instead of a normalise-and-copy pass
-  // (227 loads + 34 stores per step at n = 17 instead of 381 + 138).
-  {
-    double S = 0;
-    for (int i = 0; i < n; i++) S += v1[i];
-    uint8_t off[20], cur[19], nbr[36];
-    RB_LZ_T wgt[36];
-    for (int i = 0; i <= n; i++) off[i] = 0;
-    for (int t = 0; t < ne; t++) { off[ei[t] + 1]++; if (ej[t] != ei[t]) off[ej[t] + 1]++; }
-    for (int i = 0; i < n; i++) { off[i + 1] = (uint8_t)(off[i + 1] + off[i]); cur[i] = off[i]; }
-    double tr = 0;
-    for (int t = 0; t < ne; t++) {
-      const int a = ei[t], b = ej[t];
-      const double ewt = T.rsq[(int)v1[a]] * T.rsq[(int)v1[b]];
-      if (a == b) { nbr[cur[a]] = (uint8_t)a; wgt[cur[a]++] = (RB_LZ_T)(2.0 * ewt); tr += 2.0 * ewt; }
-      else { nbr[cur[a]] = (uint8_t)b; wgt[cur[a]++] = (RB_LZ_T)ewt; nbr[cur[b]] = (uint8_t)a; wgt[cur[b]++] = (RB_LZ_T)ewt; }
-    }
-    if (n == 2) return fabs(tr - 1.0);          // eigenvalues are 1 and trace - 1
-    const double invS = 1.0 / S;
-    for (int i = 0; i < n; i++) v1[i] = sqrt(v1[i] * invS);
-    RB_LZ_T qb[3][19];
-    double dot = 0, nrm = 0;
-    for (int i = 0; i < n; i++) dot += T.lz0[i] * v1[i];
-    for (int i = 0; i < n; i++) { const double q = T.lz0[i] - dot * v1[i]; qb[0][i] = (RB_LZ_T)q; nrm += (double)qb[0][i] * qb[0][i]; qb[1][i] = 0; }
-    int c = 0, pr = 1, nx = 2;
-    double sc = 1.0 / sqrt(nrm), sp = 0.0;       // scales of the current / previous buffer
-    RB_TD_T d[19 + GF_EXTRA_STEPS], e[19 + GF_EXTRA_STEPS];
-    int m = 0, jmax = n - 2;
-    bool extended = false;
-    e[0] = 0;
-    for (int j = 0; j <= jmax; j++) {
-      double al = 0, bt = 0, dv = 0, y2 = 0;
-      for (int i = 0; i < n; i++) {
-        double acc = 0;
-        for (int k = off[i]; k < off[i + 1]; k++) acc += (double)wgt[k] * (double)qb[c][nbr[k]];
-        const RB_LZ_T yf = (RB_LZ_T)(acc * sc);
-        const double y = yf;
-        qb[nx][i] = yf;
-        al += (double)qb[c][i] * y; bt += (double)qb[pr][i] * y; dv += (double)v1[i] * y; y2 += y * y;
-      }
-      al *= sc; bt *= sp;
-      const double ca = al * sc, cb = bt * sp;
-      double nb2 = 0;
-      for (int i = 0; i < n; i++) {
-        const double zi = (double)qb[nx][i] - ca * (double)qb[c][i] - cb * (double)qb[pr][i] - dv * (double)v1[i];
-        const RB_LZ_T zf = (RB_LZ_T)zi;
-        qb[nx][i] = zf;
-        nb2 += (double)zf * zf;
-      }
-#if GF_SECOND_ROUND
-      if (nb2 < GF_SECOND_ROUND_RATIO * y2) {     // heavy cancellation: orthogonalise once more
-        double a2 = 0, b2 = 0, d2 = 0;
-        for (int i = 0; i < n; i++) { const double z = qb[nx][i]; a2 += (double)qb[c][i] * z; b2 += (double)qb[pr][i] * z; d2 += (double)v1[i] * z; }
-        a2 *= sc; b2 *= sp;
-        const double ca2 = a2 * sc, cb2 = b2 * sp;
-        nb2 = 0;
-        for (int i = 0; i < n; i++) {
-          const double zi = (double)qb[nx][i] - ca2 * (double)qb[c][i] - cb2 * (double)qb[pr][i] - d2 * (double)v1[i];
-          const RB_LZ_T zf = (RB_LZ_T)zi;
-          qb[nx][i] = zf;
-          nb2 += (double)zf * zf;
-        }
-      }
-#endif
-      d[m] = (RB_TD_T)al; m++;
-      const double nb = sqrt(nb2);
-      if (nb < GF_BREAKDOWN) break;             // invariant subspace reached
-      if (j >= jmax) break;
-      if (nb < GF_SMALL_BETA && !extended && n > 4) { extended = true; jmax += GF_EXTRA_STEPS; }
-      e[m] = (RB_TD_T)nb;
-      const int t = pr; pr = c; c = nx; nx = t;
-      sp = sc; sc = 1.0 / nb;
-    }
-    if (m <= 2) {
-      double hi2 = d[0], lo2 = d[0];
-      if (m == 2) {
-        const double mid = 0.5 * ((double)d[0] + d[1]), hd = 0.5 * ((double)d[0] - d[1]), rad = sqrt(hd * hd + (double)e[1] * e[1]);
-        hi2 = mid + rad; lo2 = mid - rad;
-      }
-      return fmax(fabs(hi2), fabs(lo2));
-    }
-    double hi, lo;
-    tridiag_extreme_pair(d, e, m, &hi, &lo);
-    return fmax(fabs(hi), fabs(lo));
-  }
-#else
   // row sums are small integers (<= 36): 1/sqrt from a table
   double S = 0, tr = 0;
   for (int i = 0; i < n; i++) S += v1[i];
@@ -376,7 +278,6 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const TT& T, int s)
     if (m == n - 1) break;
   }
   return best;
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------
