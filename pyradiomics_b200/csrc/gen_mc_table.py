@@ -7,11 +7,12 @@ NOT transcribe that table.  It rebuilds the triangulation from geometry:
   1. corners i <-> (z, y, x) = (i>>2 & 1, i>>1 & 1, i & 1); 12 edges between corners differing in one bit;
   2. on every cube face the active edge midpoints are joined by segments (1 or 3 inside corners: one
      segment; 2 adjacent: one; 2 diagonal: two segments, either pairing -- the ambiguous face);
-  3. the segments close into polygons; every polygon is triangulated (all triangulations, both
-     orientations are candidates);
+  3. the segments close into polygons; every polygon is triangulated (all triangulations are candidates)
+     and oriented with its normals pointing from the inside corners to the outside ones (shape.py:24-27);
   4. the candidate whose (surface area, signed origin volume) equals the reference's output for that
      single-cube mask under three spacings (tests/golden/shape_cube_probes.npz, produced by
-     tests/golden/make_golden.py from the compiled reference) is kept.
+     tests/golden/make_golden.py from the compiled reference) is kept -- this pins the pairing on ambiguous
+     faces and the split of non-planar polygons, the only freedom a midpoint marching cube has.
 
 Area is additive per cube; the volume of a closed mesh depends on the per-cube triangles only through
 their origin volume at offset 0 and their vector area (fixed by the polygon boundaries), so matching the
@@ -129,6 +130,26 @@ def measure(tris, spacing):
     return area, vol6
 
 
+def orient_outward(tris, cfg):
+    """order every triangle so that its normal (a - c) x (b - c) points from the inside corners to the outside
+    ones (the reference's convention, shape.py:24-27): every mesh vertex sits on an edge with one inside and one
+    outside corner, and the normal must have a positive component along (outside - inside) summed over the
+    triangle's three vertices.  The probes only see the origin volume of a cube at offset 0, which cannot tell a
+    polygon from its mirror-oriented twin when two polygons have equal and opposite origin volumes; the whole-mesh
+    volume (origin volume + offset . vector area) can."""
+    out = []
+    for t in tris:
+        pts = [np.array(EDGE_MID2[e], dtype=float) * 0.5 for e in t]
+        nrm = np.cross(pts[0] - pts[2], pts[1] - pts[2])
+        d = np.zeros(3)
+        for e in t:
+            a, b = EDGES[e]
+            ins, outs = (a, b) if cfg >> a & 1 else (b, a)
+            d += np.array(corner(outs), dtype=float) - np.array(corner(ins), dtype=float)
+        out.append(t if float(np.dot(nrm, d)) > 0 else (t[0], t[2], t[1]))
+    return out
+
+
 def build():
     pr = np.load(PROBES)
     spacings, probes = pr["spacings"], pr["probes"]
@@ -145,9 +166,8 @@ def build():
                 for poly in polygons(segs):
                     cands = []
                     for tri in triangulations(poly):
-                        for orient in (1, -1):
-                            tt = [t if orient == 1 else (t[0], t[2], t[1]) for t in tri]
-                            cands.append((tt, np.array([measure(tt, sp) for sp in spacings])))
+                        tt = orient_outward(tri, cfg)
+                        cands.append((tt, np.array([measure(tt, sp) for sp in spacings])))
                     cand_sets.append(cands)
             for combo in itertools.product(*cand_sets):
                 tot = sum((c[1] for c in combo), np.zeros((3, 2)))

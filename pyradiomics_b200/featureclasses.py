@@ -160,8 +160,8 @@ class RadiomicsFeaturesBase:
         for feature, enabled in self.enabledFeatures.items():
             if not enabled:
                 continue
-            if self.featureNames.get(feature):
-                self.logger.debug("Feature %s is deprecated", feature)
+            if self.featureNames.get(feature) and feature not in vals:
+                self.logger.debug("Feature %s is deprecated", feature)     # texture: the reference raises DeprecationWarning
                 continue
             try:
                 self.featureValues[feature] = np.squeeze(np.float64(vals[feature]))
@@ -416,10 +416,79 @@ class RadiomicsFirstOrder(RadiomicsFeaturesBase):
 _add_feature_getters(RadiomicsFirstOrder, RadiomicsFirstOrder.NAMES,
                      deprecated=[("StandardDeviation", "the square root of Variance")])
 
+class RadiomicsShape(RadiomicsFeaturesBase):
+    """3-D shape descriptors of the ROI (reference radiomics/shape.py): mesh
+    surface area / volume / maximum diameters from the CUDA marching-cubes + all-pairs kernels
+    (rb_shape_coefficients_dev), axis lengths from exact integer voxel moments (rb_shape_moments_dev).
+    Segment-based only, like the reference (shape.py:50-52); independent of gray values (no binning)."""
+    CLASS, MATRIX_ATTR = "shape", "_unused_matrix"
+    NAMES = ["MeshVolume", "VoxelVolume", "SurfaceArea", "SurfaceVolumeRatio", "Sphericity", "Maximum3DDiameter",
+             "Maximum2DDiameterSlice", "Maximum2DDiameterColumn", "Maximum2DDiameterRow", "MajorAxisLength",
+             "MinorAxisLength", "LeastAxisLength", "Elongation", "Flatness"]
+    DEPRECATED = ["Compactness1", "Compactness2", "SphericalDisproportion"]
+
+    def __init__(self, inputImage, inputMask, **kwargs):
+        if np.ndim(I.as_array(inputMask)) != 3:
+            raise AssertionError("Shape features are only available in 3D. If 2D, use shape2D instead")
+        super().__init__(inputImage, inputMask, **kwargs)
+
+    def _applyBinning(self, matrix):          # shape ignores intensities
+        return matrix
+
+    def _calculateVoxels(self):
+        raise NotImplementedError("Shape features are not available in voxel-based mode")
+
+    def _initCalculation(self, voxelCoordinates=None):
+        from . import cshape
+        self.pixelSpacing = np.array(self._spacing_zyx(), dtype=np.float64)
+        # pad with one plane of zeros on every side (shape.py:58-72): every ROI voxel gets its 8 cubes
+        padded = np.pad(np.asarray(self.maskArray, dtype=np.uint8), 1)
+        self.maskArray = padded != 0
+        m_t = imageoperations._to_device(padded)
+        self.SurfaceArea, self.Volume, self.diameters, self._n_vertices = cshape.coefficients_device(m_t, self.pixelSpacing)
+        mom = cshape.moments_device(m_t)
+        self._Np = mom[0]
+        self.eigenValues = cshape.covariance_eigenvalues(mom, self.pixelSpacing)
+
+    def _segment_features(self):
+        sa, vol, ev = self.SurfaceArea, self.Volume, self.eigenValues
+        with np.errstate(divide="ignore", invalid="ignore"):
+            sph = np.float64(36 * np.pi * vol ** 2) ** (1.0 / 3.0)
+            f = {"MeshVolume": vol, "VoxelVolume": self._Np * float(np.multiply.reduce(self.pixelSpacing)), "SurfaceArea": sa,
+                 "SurfaceVolumeRatio": np.float64(sa) / vol, "Sphericity": sph / sa,
+                 "Compactness1": vol / (np.float64(sa) ** 1.5 * np.sqrt(np.pi)),
+                 "Compactness2": 36.0 * np.pi * vol ** 2 / np.float64(sa) ** 3, "SphericalDisproportion": sa / sph,
+                 "Maximum3DDiameter": self.diameters[3], "Maximum2DDiameterSlice": self.diameters[0],
+                 "Maximum2DDiameterColumn": self.diameters[1], "Maximum2DDiameterRow": self.diameters[2]}
+            for name, k in (("MajorAxisLength", 2), ("MinorAxisLength", 1), ("LeastAxisLength", 0)):
+                f[name] = np.nan if ev[k] < 0 else np.sqrt(ev[k]) * 4            # shape.py:313-371
+            f["Elongation"] = np.nan if (ev[1] < 0 or ev[2] < 0) else np.sqrt(ev[1] / ev[2])
+            f["Flatness"] = np.nan if (ev[0] < 0 or ev[2] < 0) else np.sqrt(ev[0] / ev[2])
+        return f
+
+    def _value(self, name):
+        if not hasattr(self, "SurfaceArea"):
+            self._initCalculation()
+        return np.float64(self._segment_features()[name])
+
+
+def _add_shape_getters():
+    _add_feature_getters(RadiomicsShape, RadiomicsShape.NAMES)
+    for n in RadiomicsShape.DEPRECATED:       # still computable on request, skipped by enableAllFeatures (shape.py:203-273)
+        def getter(self, _n=n):
+            return self._value(_n)
+        getter.__name__ = f"get{n}FeatureValue"
+        getter.__doc__ = f"SHAPE {n} (deprecated in the reference: correlated to Sphericity)."
+        getter._is_deprecated = True
+        setattr(RadiomicsShape, getter.__name__, getter)
+
+
+_add_shape_getters()
+
 FEATURE_CLASSES = {"glcm": RadiomicsGLCM, "glrlm": RadiomicsGLRLM, "glszm": RadiomicsGLSZM, "gldm": RadiomicsGLDM,
                    "ngtdm": RadiomicsNGTDM}
 # next row of the hot-path table (SURVEY.md section 8f): registered by install() as well
-NEXT_CLASSES = {"firstorder": RadiomicsFirstOrder}
+NEXT_CLASSES = {"firstorder": RadiomicsFirstOrder, "shape": RadiomicsShape}
 
 
 def install(radiomics_module=None):
@@ -433,6 +502,8 @@ def install(radiomics_module=None):
     for name, cls in {**FEATURE_CLASSES, **NEXT_CLASSES}.items():
         classes[name] = cls
     rad.cMatrices = cmatrices
+    from . import cshape
+    rad.cShape = cshape          # calculate_coefficients (3-D); the 2-D variant stays with the reference
     for mod in ("glcm", "glrlm", "glszm", "gldm", "ngtdm", "firstorder"):
         try:
             importlib.import_module(f"{rad.__name__}.{mod}").cMatrices = cmatrices
