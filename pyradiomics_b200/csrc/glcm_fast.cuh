@@ -153,17 +153,28 @@ RB_HD void glcm_solve_tables_from(const GlcmFastTables& T, GlcmSolveTables& S) {
   for (int i = 0; i < GF_LOGT; i++) S.rsq[i] = T.rsq[i];
 }
 
+// scr: per-thread float scratch of GF_LZ_SCRATCH elements with element stride st (device: shared
+// memory, [element][thread] so a warp's accesses never conflict; host / generic callers: a local buffer,
+// st = 1).  Shared memory instead of per-thread local arrays: ncu showed 11.6 long-scoreboard stall
+// cycles per issue from local-memory L1 misses (32 warps x ~0.7 KB each do not fit L1).
+constexpr int GF_LZ_SCRATCH = 4 * 19 + 18 + 2 * (19 + GF_EXTRA_STEPS);
 template <class TT>
-RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const TT& T, int s) {
+RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const TT& T, int s, RB_LZ_T* scr, int st) {
+#define v1(i) scr[(i) * st]
+#define q0(i) scr[(19 + (i)) * st]
+#define q1(i) scr[(38 + (i)) * st]
+#define z(i) scr[(57 + (i)) * st]
+#define ew(i) scr[(76 + (i)) * st]
+  RB_LZ_T* const d = scr + 94 * st;
+  RB_LZ_T* const e = scr + (94 + 19 + GF_EXTRA_STEPS) * st;
   const int np = T.np[s];
   const uint8_t* pA = T.pA[s];
   const uint8_t* pB = T.pB[s];
   // level nodes (<= 19 for a connected graph with <= 18 edges), R = endpoint multiplicity = row sum
   // stored in float (halves the per-thread scratch that has to stay in L1); all arithmetic in double
-  RB_LZ_T v1[19], q0[19], q1[19], z[19], ew[18];
   uint8_t nodelev[19], ei[18], ej[18];
   int n = 0, ne = 0;
-  for (int i = 0; i < 19; i++) v1[i] = 0;
+  for (int i = 0; i < 19; i++) v1(i) = 0;
   for (int t = 0; t < np; t++) {
     const uint8_t a = w[pA[t] * ws], b = w[pB[t] * ws];
     if (!a || !b) continue;
@@ -173,7 +184,7 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const TT& T, int s)
     for (; j < n; j++) if (nodelev[j] == b) break;
     if (j == n) { if (n >= 19) return 1.0; nodelev[n++] = b; }
     ei[ne] = (uint8_t)i; ej[ne] = (uint8_t)j; ne++;
-    v1[i] += 1.0; v1[j] += 1.0;
+    v1(i) += 1.0; v1(j) += 1.0;
   }
   if (n < 2) return 0.0;
   {
@@ -198,14 +209,14 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const TT& T, int s)
   }
   // row sums are small integers (<= 36): 1/sqrt from a table
   double S = 0, tr = 0;
-  for (int i = 0; i < n; i++) S += v1[i];
+  for (int i = 0; i < n; i++) S += v1(i);
   for (int t = 0; t < ne; t++) {
-    ew[t] = T.rsq[(int)v1[ei[t]]] * T.rsq[(int)v1[ej[t]]];
-    if (ei[t] == ej[t]) tr += 2.0 * ew[t];      // trace of M
+    ew(t) = T.rsq[(int)v1(ei[t])] * T.rsq[(int)v1(ej[t])];
+    if (ei[t] == ej[t]) tr += 2.0 * ew(t);      // trace of M
   }
   if (n == 2) return fabs(tr - 1.0);          // eigenvalues are 1 and trace - 1
   const double invS = 1.0 / S;
-  for (int i = 0; i < n; i++) v1[i] = sqrt(v1[i] * invS);
+  for (int i = 0; i < n; i++) v1(i) = sqrt(v1(i) * invS);
   // Lanczos from a fixed pseudo-random start vector projected off v1.  If the recurrence breaks
   // down before n-1 steps the Ritz values found are still exact eigenvalues; with unstructured
   // start components a breakdown means repeated eigenvalues, not a missed one (60000 random and
@@ -215,55 +226,54 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const TT& T, int s)
   for (int attempt = 0; attempt < GF_LANCZOS_ATTEMPTS; attempt++) {
     double dot = 0, nrm = 0;
     for (int i = 0; i < n; i++) {
-      q1[i] = attempt == 0 ? T.lz0[i] : T.lz1[i];
-      dot += q1[i] * v1[i];
+      q1(i) = attempt == 0 ? T.lz0[i] : T.lz1[i];
+      dot += q1(i) * v1(i);
     }
-    for (int i = 0; i < n; i++) { q1[i] -= dot * v1[i]; nrm += q1[i] * q1[i]; q0[i] = 0; }
+    for (int i = 0; i < n; i++) { q1(i) -= dot * v1(i); nrm += q1(i) * q1(i); q0(i) = 0; }
     nrm = 1.0 / sqrt(nrm);
-    for (int i = 0; i < n; i++) q1[i] *= nrm;
-    RB_TD_T d[19 + GF_EXTRA_STEPS], e[19 + GF_EXTRA_STEPS];
+    for (int i = 0; i < n; i++) q1(i) *= nrm;
     double beta = 0;
     int m = 0;
-    e[0] = 0;
+    e[(0) * st] = 0;
     int jmax = n - 2;
     bool extended = false;
     for (int j = 0; j <= jmax; j++) {
-      for (int i = 0; i < n; i++) z[i] = 0;
+      for (int i = 0; i < n; i++) z(i) = 0;
       for (int t = 0; t < ne; t++) {
         const int a = ei[t], b = ej[t];
-        z[a] += ew[t] * q1[b];
-        z[b] += ew[t] * q1[a];
+        z(a) += ew(t) * q1(b);
+        z(b) += ew(t) * q1(a);
       }
       double alpha = 0;
-      for (int i = 0; i < n; i++) alpha += q1[i] * z[i];
+      for (int i = 0; i < n; i++) alpha += q1(i) * z(i);
       double dv = 0;
-      for (int i = 0; i < n; i++) { z[i] -= alpha * q1[i] + beta * q0[i]; dv += z[i] * v1[i]; }
+      for (int i = 0; i < n; i++) { z(i) -= alpha * q1(i) + beta * q0(i); dv += z(i) * v1(i); }
 #if GF_LOCAL_REORTH
       // re-orthogonalise against the deflated vector and the last two Lanczos vectors
       double c1 = 0, c0 = 0;
-      for (int i = 0; i < n; i++) { z[i] -= dv * v1[i]; c1 += z[i] * q1[i]; c0 += z[i] * q0[i]; }
+      for (int i = 0; i < n; i++) { z(i) -= dv * v1(i); c1 += z(i) * q1(i); c0 += z(i) * q0(i); }
       double nb = 0;
-      for (int i = 0; i < n; i++) { z[i] -= c1 * q1[i] + c0 * q0[i]; nb += z[i] * z[i]; }
+      for (int i = 0; i < n; i++) { z(i) -= c1 * q1(i) + c0 * q0(i); nb += z(i) * z(i); }
 #else
       // keep the iterate orthogonal to the deflated (known) eigenvector
       double nb = 0;
-      for (int i = 0; i < n; i++) { const double zi = z[i] - dv * v1[i]; z[i] = zi; nb += zi * zi; }
+      for (int i = 0; i < n; i++) { const double zi = z(i) - dv * v1(i); z(i) = zi; nb += zi * zi; }
 #endif
-      d[m] = alpha; m++;
+      d[(m) * st] = alpha; m++;
       nb = sqrt(nb);
       if (nb < GF_BREAKDOWN) break;             // invariant subspace reached
       // a small beta amplifies the rounding of the float-stored vectors (orthogonality is lost and
       // n-1 steps no longer span the space): such tasks run GF_EXTRA_STEPS more steps
       if (j >= jmax) break;
       if (nb < GF_SMALL_BETA && !extended && n > 4) { extended = true; jmax += GF_EXTRA_STEPS; }
-      e[m] = nb; beta = nb;
+      e[(m) * st] = nb; beta = nb;
       const double inb = 1.0 / nb;
-      for (int i = 0; i < n; i++) { q0[i] = q1[i]; q1[i] = z[i] * inb; }
+      for (int i = 0; i < n; i++) { q0(i) = q1(i); q1(i) = z(i) * inb; }
     }
     if (m <= 2) {                             // closed forms for 1x1 / 2x2
-      double hi2 = d[0], lo2 = d[0];
+      double hi2 = d[(0) * st], lo2 = d[(0) * st];
       if (m == 2) {
-        const double mid = 0.5 * ((double)d[0] + d[1]), hd = 0.5 * ((double)d[0] - d[1]), rad = sqrt(hd * hd + (double)e[1] * e[1]);
+        const double mid = 0.5 * ((double)d[(0) * st] + d[(1) * st]), hd = 0.5 * ((double)d[(0) * st] - d[(1) * st]), rad = sqrt(hd * hd + (double)e[(1) * st] * e[(1) * st]);
         hi2 = mid + rad; lo2 = mid - rad;
       }
       best = fmax(best, fmax(fabs(hi2), fabs(lo2)));
@@ -273,11 +283,22 @@ RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const TT& T, int s)
     // both extreme eigenvalues of the deflated tridiagonal in one Laguerre loop (the Lanczos betas
     // are > 1e-10, so T is unreduced: simple eigenvalues)
     double hi, lo;
-    tridiag_extreme_pair(d, e, m, &hi, &lo);
+    tridiag_extreme_pair(d, e, m, &hi, &lo, st);
     best = fmax(best, fmax(fabs(hi), fabs(lo)));
     if (m == n - 1) break;
   }
   return best;
+#undef v1
+#undef q0
+#undef q1
+#undef z
+#undef ew
+}
+// convenience: private scratch (host emulation, generic callers)
+template <class TT>
+RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const TT& T, int s) {
+  RB_LZ_T scr[GF_LZ_SCRATCH];
+  return glcm_fast_solve_task(w, ws, T, s, scr, 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -340,8 +361,10 @@ RB_HD double tridiag_bisect_static(const double* d, const double* e, double lo, 
   }
   return 0.5 * (lo + hi);
 }
-template <int N>
-RB_HD void tridiag_extreme_pair_static(const double* d, const double* e, double* hi_out, double* lo_out) {
+// SYNC (device, block-uniform callers only): the iteration count is agreed across the block and every
+// iteration starts at a barrier, so the block's warps stream this code together (see RB_ANGLE_SYNC).
+template <int N, bool SYNC>
+RB_HD void tridiag_extreme_pair_static(const double* d, const double* e, double* hi_out, double* lo_out, bool live) {
   double lo = d[0], hi = d[0];
 #pragma unroll
   for (int i = 0; i < N; i++) {
@@ -349,8 +372,13 @@ RB_HD void tridiag_extreme_pair_static(const double* d, const double* e, double*
     lo = fmin(lo, d[i] - r); hi = fmax(hi, d[i] + r);
   }
   double x[2] = {hi + 1e-9, lo - 1e-9};
-  bool done[2] = {false, false};
-  for (int it = 0; it < 24 && !(done[0] && done[1]); it++) {
+  bool done[2] = {!live, !live};
+  for (int it = 0; it < 24; it++) {
+    const bool pending = !(done[0] && done[1]);
+#ifdef __CUDA_ARCH__
+    if (SYNC) { if (!__syncthreads_or(pending)) break; } else
+#endif
+    if (!pending) break;
 #pragma unroll
     for (int c = 0; c < 2; c++) {
       double p0 = 1.0, p1 = d[0] - x[c], q0 = 0.0, q1 = -1.0, r0 = 0.0, r1 = 0.0;   // p, p', p''
@@ -376,12 +404,19 @@ RB_HD void tridiag_extreme_pair_static(const double* d, const double* e, double*
   }
   *hi_out = done[0] ? x[0] : tridiag_bisect_static<N>(d, e, lo - 1e-9, hi + 1e-9, N - 1);
   *lo_out = done[1] ? x[1] : tridiag_bisect_static<N>(d, e, lo - 1e-9, hi + 1e-9, 0);
+  if (!live) { *hi_out = 0; *lo_out = 0; }
 }
 
 // second largest |eigenvalue| of the normalised co-occurrence matrix of angle slot s whose level
 // graph has at most N nodes.  *ok = false (nothing computed) if it has more.
-template <int N, class TT>
-RB_HD double glcm_small_solve(const uint8_t* w, int ws, const uint32_t* W7, const TT& T, int s, bool* ok) {
+#ifdef __CUDA_ARCH__
+#define RB_SOLVE_SYNC() do { if (SYNC) __syncthreads(); } while (0)
+#else
+#define RB_SOLVE_SYNC() do { } while (0)
+#endif
+template <int N, bool SYNC = false, class TT>
+RB_HD double glcm_small_solve(const uint8_t* w, int ws, const uint32_t* W7, const TT& T, int s, bool* ok, bool live = true) {
+  RB_SOLVE_SYNC();
   const int dsh = T.dshift[s];
   const uint32_t NZ = ~glcm_eq_positions(W7, 0u) & 0x7FFFFFFu;
   const uint32_t VL = NZ & (NZ >> dsh) & T.lo_mask[s];        // valid pairs, by their lower position
@@ -396,8 +431,10 @@ RB_HD double glcm_small_solve(const uint8_t* w, int ws, const uint32_t* W7, cons
     Eh[i] = (E >> dsh) & VL;        // pairs whose upper end is in class i
     R[i] = RB_POPC(El[i]) + RB_POPC(Eh[i]);
   }
-  if (U) { *ok = false; return 0.0; }
-  *ok = true;
+  *ok = U == 0;
+  if (!SYNC && U) return 0.0;                 // (block-uniform callers carry on: no divergent exit before a barrier)
+  if (U) live = false;
+  RB_SOLVE_SYNC();
   const double invS = 1.0 / (2.0 * RB_POPC(VL));
   double v1[N], rs[N];
 #pragma unroll
@@ -416,6 +453,7 @@ RB_HD double glcm_small_solve(const uint8_t* w, int ws, const uint32_t* W7, cons
   e[0] = 0;
 #pragma unroll
   for (int k = 0; k + 2 < N; k++) {
+    RB_SOLVE_SYNC();
     double sigma = 0;
 #pragma unroll
     for (int i = k + 2; i < N; i++) sigma += a[i][k] * a[i][k];
@@ -449,7 +487,8 @@ RB_HD double glcm_small_solve(const uint8_t* w, int ws, const uint32_t* W7, cons
   }
   d[N - 2] = a[N - 2][N - 2]; e[N - 1] = a[N - 1][N - 2]; d[N - 1] = a[N - 1][N - 1];
   double hi, lo;
-  tridiag_extreme_pair_static<N>(d, e, &hi, &lo);
+  RB_SOLVE_SYNC();
+  tridiag_extreme_pair_static<N, SYNC>(d, e, &hi, &lo, live);
   return fmax(fabs(hi), fabs(lo));
 }
 
@@ -457,7 +496,7 @@ RB_HD double glcm_small_solve(const uint8_t* w, int ws, const uint32_t* W7, cons
 // handles: 0: n <= 8 and 1: n <= 12 (dense register solves), 2: larger graphs (sparse Lanczos),
 // -1: any (host emulation).
 template <int KIND, class TT>
-RB_HD double glcm_fast_solve(const uint8_t* w, int ws, const TT& T, int s, int cls) {
+RB_HD double glcm_fast_solve(const uint8_t* w, int ws, const TT& T, int s, int cls, RB_LZ_T* scr = nullptr, int st = 1) {
 #if GF_DENSE_SMALL
   if ((KIND == 0 || KIND == 1 || KIND == -1) && cls <= GF_DENSE_MAX_CLS) {
     uint32_t W7[7];
@@ -477,6 +516,7 @@ RB_HD double glcm_fast_solve(const uint8_t* w, int ws, const TT& T, int s, int c
   }
 #endif
   if (KIND == 0 || KIND == 1) return NAN;
+  if (KIND == 2) return glcm_fast_solve_task(w, ws, T, s, scr, st);       // device: shared-memory scratch
   return glcm_fast_solve_task(w, ws, T, s);
 }
 

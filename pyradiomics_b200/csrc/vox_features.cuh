@@ -236,21 +236,21 @@ static RB_HDN double tridiag_extreme_eigenvalue(const TD* d, const TD* e, int n,
 // Both extreme eigenvalues of an unreduced symmetric tridiagonal in one Laguerre loop (one pass over
 // d, e per iteration serves both ends; lanes of a warp do not serialise "top" and "bottom" calls).
 template <typename TD>
-static RB_HDN void tridiag_extreme_pair(const TD* d, const TD* e, int n, double* hi_out, double* lo_out) {
-  double lo = d[0], hi = d[0];
+static RB_HDN void tridiag_extreme_pair(const TD* d, const TD* e, int n, double* hi_out, double* lo_out, int st = 1) {
+  double lo = d[(0) * st], hi = d[(0) * st];
   for (int i = 0; i < n; i++) {
-    const double r = (i > 0 ? fabs((double)e[i]) : 0.0) + (i + 1 < n ? fabs((double)e[i + 1]) : 0.0);
-    lo = fmin(lo, d[i] - r); hi = fmax(hi, d[i] + r);
+    const double r = (i > 0 ? fabs((double)e[(i) * st]) : 0.0) + (i + 1 < n ? fabs((double)e[(i + 1) * st]) : 0.0);
+    lo = fmin(lo, d[(i) * st] - r); hi = fmax(hi, d[(i) * st] + r);
   }
-  if (n == 1) { *hi_out = d[0]; *lo_out = d[0]; return; }
+  if (n == 1) { *hi_out = d[(0) * st]; *lo_out = d[(0) * st]; return; }
   double xh = hi + 1e-9, xl = lo - 1e-9;
   bool dh = false, dl = false;
   for (int it = 0; it < 40 && !(dh && dl); it++) {
-    const double d0 = d[0];
+    const double d0 = d[(0) * st];
     double hp0 = 1.0, hp1 = d0 - xh, hq0 = 0.0, hq1 = -1.0, hr0 = 0.0, hr1 = 0.0;
     double lp0 = 1.0, lp1 = d0 - xl, lq0 = 0.0, lq1 = -1.0, lr0 = 0.0, lr1 = 0.0;
     for (int i = 1; i < n; i++) {
-      const double di = d[i], b = (double)e[i] * (double)e[i];
+      const double di = d[(i) * st], b = (double)e[(i) * st] * (double)e[(i) * st];
       {
         const double a = di - xh;
         const double p2 = a * hp1 - b * hp0, q2 = a * hq1 - hp1 - b * hq0, r2 = a * hr1 - 2.0 * hq1 - b * hr0;
@@ -289,8 +289,11 @@ static RB_HDN void tridiag_extreme_pair(const TD* d, const TD* e, int n, double*
       }
     }
   }
-  *hi_out = dh ? xh : tridiag_kth_eigenvalue(d, e, n, n - 1, lo - 1e-9, hi + 1e-9, 40);
-  *lo_out = dl ? xl : tridiag_kth_eigenvalue(d, e, n, 0, lo - 1e-9, hi + 1e-9, 40);
+  if (dh && dl) { *hi_out = xh; *lo_out = xl; return; }
+  double dc[24], ec[24];                       // rare: Sturm bisection on a contiguous copy
+  for (int i = 0; i < n && i < 24; i++) { dc[i] = d[i * st]; ec[i] = e[i * st]; }
+  *hi_out = dh ? xh : tridiag_kth_eigenvalue(dc, ec, n, n - 1, lo - 1e-9, hi + 1e-9, 40);
+  *lo_out = dl ? xl : tridiag_kth_eigenvalue(dc, ec, n, 0, lo - 1e-9, hi + 1e-9, 40);
 }
 
 // Second-largest eigenvalue of a symmetric positive semi-definite matrix with spectrum in [0, 1+]

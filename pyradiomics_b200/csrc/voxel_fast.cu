@@ -108,11 +108,14 @@ glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ ce
 // Phase B.  KIND 0: tasks with n <= 8 levels, KIND 1: 9..12 (dense register solves, see
 // glcm_small_solve), KIND 2: larger level graphs (sparse Lanczos with per-thread scratch).  Each is
 // its own kernel because the three want very different register budgets.
+#ifndef GF_DENSE_SYNC
+#define GF_DENSE_SYNC 1
+#endif
 #ifndef GF_SOLVE_MINB_S
 #define GF_SOLVE_MINB_S 4
 #endif
 #ifndef GF_SOLVE_MINB_L
-#define GF_SOLVE_MINB_L 8
+#define GF_SOLVE_MINB_L 3
 #endif
 #ifndef GF_SOLVE_TILE
 #define GF_SOLVE_TILE 2048
@@ -121,6 +124,43 @@ template <int KIND> struct SolveKind;
 template <> struct SolveKind<0> { static constexpr int lo = 0, hi = 6, minb = GF_SOLVE_MINB_S; };
 template <> struct SolveKind<1> { static constexpr int lo = 7, hi = GF_DENSE_MAX_CLS, minb = 2; };
 template <> struct SolveKind<2> { static constexpr int lo = GF_DENSE_MAX_CLS + 1, hi = GF_NCLS - 1, minb = GF_SOLVE_MINB_L; };
+
+// the 27 window levels of the voxel with linear index vi (zeros if !live)
+__device__ __forceinline__ void glcm_task_window(const uint8_t* __restrict__ lev, const VoxParams& P, long long vi, bool live,
+                                                 uint8_t* w) {
+  const int z = (int)(vi / P.sz), rem = (int)(vi % P.sz), y = rem / (int)P.sy, x = rem % (int)P.sy;
+  int p = 0;
+#pragma unroll
+  for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+      for (int dx = -1; dx <= 1; dx++, p++) {
+        const int zz = z + dz, yy = y + dy, xx = x + dx;
+        const bool in = live && zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
+        w[p] = in ? lev[vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : (uint8_t)0;
+      }
+}
+
+// sorted positions [begin, end) of the tile: tasks whose level graph has at most N nodes
+template <int N>
+__device__ __forceinline__ void solve_group(const uint8_t* __restrict__ lev, const VoxParams& P, const GlcmSolveTables& T,
+                                            const GlcmTask* __restrict__ queue, double* __restrict__ res,
+                                            const uint16_t* order, unsigned base, int begin, int end) {
+  for (int b0 = begin; b0 < end; b0 += 128) {              // block-uniform bounds
+    const int i = b0 + (int)threadIdx.x;
+    const bool live = i < end;
+    const unsigned k = base + order[live ? i : begin];
+    const GlcmTask e = queue[k];
+    uint8_t w[27];
+    glcm_task_window(lev, P, e.vi, live, w);
+    uint32_t W7[7];
+    glcm_pack_window(w, 1, W7);
+    bool ok;
+    const double r = glcm_small_solve<N, GF_DENSE_SYNC != 0>(w, 1, W7, T, e.slot, &ok, live);
+    if (live) res[k] = ok ? r : NAN;
+  }
+}
 
 template <int KIND>
 __global__ void __launch_bounds__(128, SolveKind<KIND>::minb)
@@ -164,23 +204,27 @@ glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ 
       if (mycls[j] >= SolveKind<KIND>::lo && mycls[j] <= SolveKind<KIND>::hi)
         order[atomicAdd(&bucket[mycls[j]], 1)] = (uint16_t)(j * 128 + threadIdx.x);
     __syncthreads();
-    for (int i = threadIdx.x; i < ntile; i += 128) {
-      const unsigned k = base + order[i];
-      const GlcmTask e = queue[k];
-      const int z = (int)(e.vi / P.sz), rem = (int)(e.vi % P.sz), y = rem / (int)P.sy, x = rem % (int)P.sy;
-      uint8_t w[27];
-      int p = 0;
-#pragma unroll
-      for (int dz = -1; dz <= 1; dz++)
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-          for (int dx = -1; dx <= 1; dx++, p++) {
-            const int zz = z + dz, yy = y + dy, xx = x + dx;
-            const bool in = zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
-            w[p] = in ? lev[e.vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : (uint8_t)0;
-          }
-      res[k] = glcm_fast_solve<KIND>(w, 1, T, e.slot, e.cls);
+    if (KIND == 2) {
+      extern __shared__ float lz_scratch[];              // [GF_LZ_SCRATCH][128]
+      for (int i = threadIdx.x; i < ntile; i += 128) {
+        const unsigned k = base + order[i];
+        const GlcmTask e = queue[k];
+        uint8_t w[27];
+        glcm_task_window(lev, P, e.vi, true, w);
+        res[k] = glcm_fast_solve<2>(w, 1, T, e.slot, e.cls, lz_scratch + threadIdx.x, 128);
+      }
+    } else {
+      // dense solves: one template size at a time, block-uniform (idle threads run on an empty window), so the
+      // barriers inside glcm_small_solve keep the warps on the same code (ncu: 8-10 no_instruction stall cycles
+      // per issue with free-running warps -- these bodies are 2-10 k straight-line instructions)
+      if (KIND == 0) {
+        solve_group<4>(lev, P, T, queue, res, order, base, 0, bucket[2]);
+        solve_group<6>(lev, P, T, queue, res, order, base, bucket[2], bucket[4]);
+        solve_group<8>(lev, P, T, queue, res, order, base, bucket[4], bucket[6]);
+      } else {
+        solve_group<10>(lev, P, T, queue, res, order, base, 0, bucket[8]);
+        solve_group<12>(lev, P, T, queue, res, order, base, bucket[8], bucket[GF_DENSE_MAX_CLS]);
+      }
     }
     __syncthreads();
   }
@@ -289,7 +333,13 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
     static const int solve_bps = getenv("B200_GLCM_SOLVE_BPS") ? atoi(getenv("B200_GLCM_SOLVE_BPS")) : 8;
     glcm_fast_solve_kernel<0><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
     glcm_fast_solve_kernel<1><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
-    glcm_fast_solve_kernel<2><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
+    constexpr int lz_bytes = GF_LZ_SCRATCH * 128 * (int)sizeof(float);
+    static bool lz_attr[64] = {false};
+    if (!lz_attr[dev & 63]) {
+      RB_CUDA(cudaFuncSetAttribute(glcm_fast_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lz_bytes));
+      lz_attr[dev & 63] = true;
+    }
+    glcm_fast_solve_kernel<2><<<sms * solve_bps, 128, lz_bytes, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
     RB_LAUNCH_CHECK();
     glcm_fast_finish_kernel<<<sms * 8, 256, 0, st>>>(P, Q->q, Q->count, Q->res, out + (long long)G_MCC * fstride, out_z0);
     RB_LAUNCH_CHECK();
