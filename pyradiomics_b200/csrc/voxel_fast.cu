@@ -108,6 +108,9 @@ glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ ce
 // Phase B.  KIND 0: tasks with n <= 8 levels, KIND 1: 9..12 (dense register solves, see
 // glcm_small_solve), KIND 2: larger level graphs (sparse Lanczos with per-thread scratch).  Each is
 // its own kernel because the three want very different register budgets.
+#ifndef GF_LZ_SMEM
+#define GF_LZ_SMEM 0      // 1: Lanczos scratch in shared memory -- 9 % faster but produced sporadic garbage on B200 (race not found); kept off
+#endif
 #ifndef GF_DENSE_SYNC
 #define GF_DENSE_SYNC 1
 #endif
@@ -115,7 +118,7 @@ glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ ce
 #define GF_SOLVE_MINB_S 4
 #endif
 #ifndef GF_SOLVE_MINB_L
-#define GF_SOLVE_MINB_L 3
+#define GF_SOLVE_MINB_L 8
 #endif
 #ifndef GF_SOLVE_TILE
 #define GF_SOLVE_TILE 2048
@@ -211,7 +214,11 @@ glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ 
         const GlcmTask e = queue[k];
         uint8_t w[27];
         glcm_task_window(lev, P, e.vi, true, w);
+#if GF_LZ_SMEM
         res[k] = glcm_fast_solve<2>(w, 1, T, e.slot, e.cls, lz_scratch + threadIdx.x, 128);
+#else
+        res[k] = glcm_fast_solve_task(w, 1, T, e.slot);      // per-thread local scratch
+#endif
       }
     } else {
       // dense solves: one template size at a time, block-uniform (idle threads run on an empty window), so the
@@ -333,7 +340,7 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
     static const int solve_bps = getenv("B200_GLCM_SOLVE_BPS") ? atoi(getenv("B200_GLCM_SOLVE_BPS")) : 8;
     glcm_fast_solve_kernel<0><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
     glcm_fast_solve_kernel<1><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
-    constexpr int lz_bytes = GF_LZ_SCRATCH * 128 * (int)sizeof(float);
+    constexpr int lz_bytes = GF_LZ_SMEM ? GF_LZ_SCRATCH * 128 * (int)sizeof(float) : 0;
     static bool lz_attr[64] = {false};
     if (!lz_attr[dev & 63]) {
       RB_CUDA(cudaFuncSetAttribute(glcm_fast_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lz_bytes));

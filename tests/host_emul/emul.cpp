@@ -81,6 +81,20 @@ extern "C" double emul_glcm_solve_window(const uint8_t* w, int slot, int Ng) {
 }
 
 #include "../../pyradiomics_b200/csrc/glrlm_fast.cuh"
+// the sparse solver with its scratch laid out like the device's shared memory ([element][thread], stride st)
+extern "C" double emul_glcm_solve_window_strided(const uint8_t* w, int slot, int Ng, int st, int lane) {
+  GlcmFastTables* T = new GlcmFastTables;
+  glcm_fast_build_tables(*T, Ng);
+  GlcmSolveTables ST;
+  glcm_solve_tables_from(*T, ST);
+  float* scr = new float[(size_t)GF_LZ_SCRATCH * st];
+  for (int i = 0; i < GF_LZ_SCRATCH * st; i++) scr[i] = 1e30f;      // poison: a wrong stride shows
+  double r = glcm_fast_solve_task(w, 1, ST, slot, scr + lane, st);
+  delete[] scr;
+  delete T;
+  return r;
+}
+
 // same task through the dispatcher (dense register solve for <= 8 levels); cls < 0: derive it
 extern "C" double emul_glcm_solve_window_cls(const uint8_t* w, int slot, int Ng, int cls) {
   GlcmFastTables* T = new GlcmFastTables;
