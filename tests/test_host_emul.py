@@ -133,3 +133,82 @@ def test_glcm_fast_math_equals_generic_math_on_host(emul, kind):
     for k, f in enumerate(NAMES["glcm"]):
         atol = 1e-6 if f in ("MCC", "Imc2", "Imc1") else 1e-9
         assert np.allclose(fast[k], gen[k], rtol=1e-7, atol=atol, equal_nan=True), f
+
+
+def _slot_angles():
+    """the fast path's processing order of the 13 distance-1 angles: reference order (cmatrices.c:843-860), stably
+    regrouped by the number of moving dimensions (glcm_fast_build_tables)"""
+    ang = [(z, y, x) for z in (1, 0, -1) for y in (1, 0, -1) for x in (1, 0, -1)][:13]
+    return [a for want in (1, 2, 3) for a in ang if sum(v != 0 for v in a) == want]
+
+
+def _mcc_angle_numpy(w27, a):
+    """second largest |eigenvalue| of P / sqrt(px py) for one angle of a 3x3x3 window (LAPACK), and the node count"""
+    W = w27.reshape(3, 3, 3)
+    P = np.zeros((256, 256))
+    for i in range(3):
+        for j in range(3):
+            for k in range(3):
+                ii, jj, kk = i + a[0], j + a[1], k + a[2]
+                if 0 <= ii < 3 and 0 <= jj < 3 and 0 <= kk < 3 and W[i, j, k] and W[ii, jj, kk]:
+                    P[W[i, j, k], W[ii, jj, kk]] += 1
+                    P[W[ii, jj, kk], W[i, j, k]] += 1
+    nz = P.sum(1) > 0
+    n = int(nz.sum())
+    if n < 2:
+        return None, n
+    Pn = P[nz][:, nz]
+    px = Pn.sum(1)
+    # connected graphs only (the solver is never asked otherwise)
+    reach = np.zeros(n, bool); reach[0] = True
+    for _ in range(n):
+        reach |= (Pn[reach].sum(0) > 0)
+    if not reach.all():
+        return None, n
+    ev = np.sort(np.abs(np.linalg.eigvalsh(Pn / np.sqrt(np.outer(px, px)))))[::-1]
+    return float(ev[1]), n
+
+
+def test_eigen_task_solvers_against_lapack(emul):
+    """the dense register solve (n <= 12), the sparse Lanczos solve (float-stored vectors) and the Lanczos solve with its
+    scratch laid out like device shared memory, on random / structured / holed windows, against numpy's eigvalsh"""
+    for f in ("emul_glcm_solve_window", "emul_glcm_solve_window_cls", "emul_glcm_solve_window_strided"):
+        getattr(emul, f).restype = C.c_double
+    slots = _slot_angles()
+    rng = np.random.default_rng(11)
+    worst = {"dense": 0.0, "lanczos": 0.0}
+    checked = 0
+    for it in range(400):
+        K = int(rng.integers(2, 20))
+        mode = it % 4
+        if mode == 0:
+            w = rng.integers(1, K + 1, 27)
+        elif mode == 1:
+            g = np.cumsum(rng.integers(-1, 2, 27)) + rng.integers(0, 2, 27)
+            w = g - g.min() + 1
+        elif mode == 2:
+            zz, yy, xx = np.meshgrid(range(3), range(3), range(3), indexing="ij")
+            c = rng.normal(size=3) * K / 4
+            w = np.round(c[0] * zz + c[1] * yy + c[2] * xx + rng.normal(size=(3, 3, 3)) * 0.7).reshape(27)
+            w = w - w.min() + 1
+        else:
+            w = rng.integers(1, K + 1, 27)
+            w[rng.random(27) < 0.2] = 0
+        w = np.ascontiguousarray(np.clip(w, 0, 32), dtype=np.uint8)
+        p = w.ctypes.data_as(C.c_void_p)
+        for s, a in enumerate(slots):
+            ref, n = _mcc_angle_numpy(w, a)
+            if ref is None:
+                continue
+            checked += 1
+            lz = emul.emul_glcm_solve_window(p, s, 32)
+            assert lz == emul.emul_glcm_solve_window_strided(p, s, 32, 128, 77)      # layout-independent
+            worst["lanczos"] = max(worst["lanczos"], abs(lz - ref))
+            d = emul.emul_glcm_solve_window_cls(p, s, 32, -1)
+            if n <= 12:
+                worst["dense"] = max(worst["dense"], abs(d - ref))
+            else:
+                assert d == lz
+    assert checked > 1500
+    assert worst["dense"] < 1e-9, worst
+    assert worst["lanczos"] < 2e-6, worst
