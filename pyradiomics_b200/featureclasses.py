@@ -430,6 +430,8 @@ class RadiomicsShape(RadiomicsFeaturesBase):
     def __init__(self, inputImage, inputMask, **kwargs):
         if np.ndim(I.as_array(inputMask)) != 3:
             raise AssertionError("Shape features are only available in 3D. If 2D, use shape2D instead")
+        if kwargs.get("voxelBased", False):      # the reference raises while constructing (shape.py:50-52 via base.py:66)
+            raise NotImplementedError("Shape features are not available in voxel-based mode")
         super().__init__(inputImage, inputMask, **kwargs)
 
     def _applyBinning(self, matrix):          # shape ignores intensities
