@@ -62,3 +62,15 @@ def test_oracle_features_match_reference_class(case):
         assert got[f] == pytest.approx(v, rel=1e-9), f
     for f, v in exp["baseline"].items():          # the stored CSV, at the reference's own 3 % (tests/testUtils.py:266-275)
         assert got[f] == pytest.approx(v, rel=0.03), f
+
+
+def test_committed_table_is_what_the_generator_derives():
+    """csrc/mc_table.inc is the output of gen_mc_table.build() on the committed probes (geometry + black-box selection),
+    not a hand-edited or transcribed table."""
+    import gen_mc_table as g
+    table = g.build()
+    mids, tri = g.load_table()
+    assert [tuple(m) for m in mids] == list(g.EDGE_MID2)
+    for cfg, tris in enumerate(table):
+        flat = [e for t in tris for e in t]
+        assert list(tri[cfg][:len(flat)]) == flat and (tri[cfg][len(flat):] == -1).all(), cfg
