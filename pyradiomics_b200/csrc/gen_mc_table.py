@@ -130,6 +130,18 @@ def measure(tris, spacing):
     return area, vol6
 
 
+_TRI_CACHE = {}
+_ORIENT_CACHE = {}
+
+
+def tri_measures(t, spacings):
+    """[(area, 6 * origin volume) per spacing] of ONE oriented triangle, cached"""
+    key = (t, spacings.tobytes())
+    if key not in _TRI_CACHE:
+        _TRI_CACHE[key] = np.array([measure([t], sp) for sp in spacings])
+    return _TRI_CACHE[key]
+
+
 def orient_outward(tris, cfg):
     """order every triangle so that its normal (a - c) x (b - c) points from the inside corners to the outside
     ones (the reference's convention, shape.py:24-27): every mesh vertex sits on an edge with one inside and one
@@ -139,6 +151,9 @@ def orient_outward(tris, cfg):
     volume (origin volume + offset . vector area) can."""
     out = []
     for t in tris:
+        if (t, cfg) in _ORIENT_CACHE:
+            out.append(_ORIENT_CACHE[(t, cfg)])
+            continue
         pts = [np.array(EDGE_MID2[e], dtype=float) * 0.5 for e in t]
         nrm = np.cross(pts[0] - pts[2], pts[1] - pts[2])
         d = np.zeros(3)
@@ -146,7 +161,8 @@ def orient_outward(tris, cfg):
             a, b = EDGES[e]
             ins, outs = (a, b) if cfg >> a & 1 else (b, a)
             d += np.array(corner(outs), dtype=float) - np.array(corner(ins), dtype=float)
-        out.append(t if float(np.dot(nrm, d)) > 0 else (t[0], t[2], t[1]))
+        _ORIENT_CACHE[(t, cfg)] = t if float(np.dot(nrm, d)) > 0 else (t[0], t[2], t[1])
+        out.append(_ORIENT_CACHE[(t, cfg)])
     return out
 
 
@@ -167,7 +183,7 @@ def build():
                     cands = []
                     for tri in triangulations(poly):
                         tt = orient_outward(tri, cfg)
-                        cands.append((tt, np.array([measure(tt, sp) for sp in spacings])))
+                        cands.append((tt, sum((tri_measures(t, spacings) for t in tt), np.zeros((len(spacings), 2)))))
                     cand_sets.append(cands)
             for combo in itertools.product(*cand_sets):
                 tot = sum((c[1] for c in combo), np.zeros((3, 2)))
