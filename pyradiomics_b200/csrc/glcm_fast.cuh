@@ -375,7 +375,7 @@ RB_HD void tridiag_extreme_pair_static(const double* d, const double* e, double*
   bool done[2] = {!live, !live};
   for (int it = 0; it < 24; it++) {
     const bool pending = !(done[0] && done[1]);
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) || defined(RB_EMULATE_BLOCK)
     if (SYNC) { if (!__syncthreads_or(pending)) break; } else
 #endif
     if (!pending) break;
@@ -409,7 +409,7 @@ RB_HD void tridiag_extreme_pair_static(const double* d, const double* e, double*
 
 // second largest |eigenvalue| of the normalised co-occurrence matrix of angle slot s whose level
 // graph has at most N nodes.  *ok = false (nothing computed) if it has more.
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) || defined(RB_EMULATE_BLOCK)      // RB_EMULATE_BLOCK: tests/host_emul/solve_kernel_emul.cpp
 #define RB_SOLVE_SYNC() do { if (SYNC) __syncthreads(); } while (0)
 #else
 #define RB_SOLVE_SYNC() do { } while (0)

@@ -9,6 +9,7 @@
 #include "common.cuh"
 #define RB_GLCM_BLOCK_SYNC 1   // phase A is called by all threads of a block, uniformly
 #include "glcm_fast.cuh"
+#include "glcm_solve_kernel.cuh"
 #include "glrlm_fast.cuh"
 #include "small_fast.cuh"
 #include "host_common.hpp"
@@ -17,24 +18,6 @@ namespace rb {
 
 constexpr int GF_THREADS = 128;
 
-// Two kernels per chunk of planes:
-//   A  one thread per centre voxel: window -> equality masks -> all 13 angles, every feature except
-//      the MCC eigen-solves; a voxel that needs k solves reserves k CONSECUTIVE 16-byte queue entries
-//      (voxel, angle slot, n_ok).  No local memory, no block barriers.
-//   B  one thread per queue entry (= one eigen-task): reloads the voxel's 27 levels and runs the
-//      sparse Lanczos + Sturm solver (glcm_fast_solve_task); result to res[k].
-//   C  one thread per voxel-with-tasks adds its results in slot order to the voxel's MCC (single
-//      writer, fixed order: deterministic).  Eigen-solves are needed by a few % of the
-//      (voxel, angle) pairs on noisy data and by most on smooth data; left inline they idle most
-//      lanes of a warp behind one long solve and force 255 registers on every thread.
-struct GlcmTask {
-  long long vi;        // linear index of the voxel in the level volume
-  uint8_t slot;        // angle slot to solve
-  uint8_t n_ok;        // number of non-empty angles of the voxel (the nanmean denominator)
-  uint8_t count;       // > 0 on the first task of a voxel: how many consecutive entries belong to it
-  uint8_t cls;         // size class of the task (glcm_task_class), groups similar tasks in a warp
-  float unused;
-};
 
 template <int MINB, int NT>
 __global__ void __launch_bounds__(NT, MINB)
@@ -105,137 +88,6 @@ glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ ce
   }
 }
 
-// Phase B.  KIND 0: tasks with n <= 8 levels, KIND 1: 9..12 (dense register solves, see
-// glcm_small_solve), KIND 2: larger level graphs (sparse Lanczos with per-thread scratch).  Each is
-// its own kernel because the three want very different register budgets.
-#ifndef GF_LZ_SMEM
-#define GF_LZ_SMEM 0      // 1: Lanczos scratch in shared memory -- 9 % faster but produced sporadic garbage on B200 (race not found); kept off
-#endif
-#ifndef GF_DENSE_SYNC
-#define GF_DENSE_SYNC 1
-#endif
-#ifndef GF_SOLVE_MINB_S
-#define GF_SOLVE_MINB_S 4
-#endif
-#ifndef GF_SOLVE_MINB_L
-#define GF_SOLVE_MINB_L 8
-#endif
-#ifndef GF_SOLVE_TILE
-#define GF_SOLVE_TILE 2048
-#endif
-template <int KIND> struct SolveKind;
-template <> struct SolveKind<0> { static constexpr int lo = 0, hi = 6, minb = GF_SOLVE_MINB_S; };
-template <> struct SolveKind<1> { static constexpr int lo = 7, hi = GF_DENSE_MAX_CLS, minb = 2; };
-template <> struct SolveKind<2> { static constexpr int lo = GF_DENSE_MAX_CLS + 1, hi = GF_NCLS - 1, minb = GF_SOLVE_MINB_L; };
-
-// the 27 window levels of the voxel with linear index vi (zeros if !live)
-__device__ __forceinline__ void glcm_task_window(const uint8_t* __restrict__ lev, const VoxParams& P, long long vi, bool live,
-                                                 uint8_t* w) {
-  const int z = (int)(vi / P.sz), rem = (int)(vi % P.sz), y = rem / (int)P.sy, x = rem % (int)P.sy;
-  int p = 0;
-#pragma unroll
-  for (int dz = -1; dz <= 1; dz++)
-#pragma unroll
-    for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-      for (int dx = -1; dx <= 1; dx++, p++) {
-        const int zz = z + dz, yy = y + dy, xx = x + dx;
-        const bool in = live && zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
-        w[p] = in ? lev[vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : (uint8_t)0;
-      }
-}
-
-// sorted positions [begin, end) of the tile: tasks whose level graph has at most N nodes
-template <int N>
-__device__ __forceinline__ void solve_group(const uint8_t* __restrict__ lev, const VoxParams& P, const GlcmSolveTables& T,
-                                            const GlcmTask* __restrict__ queue, double* __restrict__ res,
-                                            const uint16_t* order, unsigned base, int begin, int end) {
-  for (int b0 = begin; b0 < end; b0 += 128) {              // block-uniform bounds
-    const int i = b0 + (int)threadIdx.x;
-    const bool live = i < end;
-    const unsigned k = base + order[live ? i : begin];
-    const GlcmTask e = queue[k];
-    uint8_t w[27];
-    glcm_task_window(lev, P, e.vi, live, w);
-    uint32_t W7[7];
-    glcm_pack_window(w, 1, W7);
-    bool ok;
-    const double r = glcm_small_solve<N, GF_DENSE_SYNC != 0>(w, 1, W7, T, e.slot, &ok, live);
-    if (live) res[k] = ok ? r : NAN;
-  }
-}
-
-template <int KIND>
-__global__ void __launch_bounds__(128, SolveKind<KIND>::minb)
-glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ VoxParams P,
-                       const GlcmFastTables* __restrict__ Tg, const GlcmTask* __restrict__ queue,
-                       const unsigned* __restrict__ qcount, double* __restrict__ res) {
-  __shared__ GlcmSolveTables T;
-  if (threadIdx.x == 0) glcm_solve_tables_from(*Tg, T);
-  __syncthreads();
-  const unsigned n = *qcount;
-  // Tiles of 8 x 128 consecutive tasks are counting-sorted by size class in shared memory, so the
-  // lanes of a warp run solves of the same size (ncu: 11-14 of 32 lanes active otherwise).
-  constexpr int TILE = GF_SOLVE_TILE;
-  __shared__ uint16_t order[TILE];
-  __shared__ int bucket[GF_NCLS];
-  const unsigned ntiles = (n + TILE - 1) / TILE;
-  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const unsigned base = tile * TILE;
-    if (threadIdx.x < GF_NCLS) bucket[threadIdx.x] = 0;
-    __syncthreads();
-    uint8_t mycls[TILE / 128];
-#pragma unroll
-    for (int j = 0; j < TILE / 128; j++) {
-      const unsigned k = base + j * 128 + threadIdx.x;
-      mycls[j] = k < n ? queue[k].cls : GF_NCLS;
-      if (mycls[j] >= SolveKind<KIND>::lo && mycls[j] <= SolveKind<KIND>::hi) atomicAdd(&bucket[mycls[j]], 1);
-    }
-    __syncthreads();
-    int start = 0, ntile = 0;            // exclusive prefix of this thread's bucket (threads < GF_NCLS)
-#pragma unroll
-    for (int c = SolveKind<KIND>::lo; c <= SolveKind<KIND>::hi; c++) {
-      const int b = bucket[c];
-      if (c < (int)threadIdx.x) start += b;
-      ntile += b;
-    }
-    __syncthreads();
-    if (threadIdx.x < GF_NCLS) bucket[threadIdx.x] = start;
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < TILE / 128; j++)
-      if (mycls[j] >= SolveKind<KIND>::lo && mycls[j] <= SolveKind<KIND>::hi)
-        order[atomicAdd(&bucket[mycls[j]], 1)] = (uint16_t)(j * 128 + threadIdx.x);
-    __syncthreads();
-    if (KIND == 2) {
-      extern __shared__ float lz_scratch[];              // [GF_LZ_SCRATCH][128]
-      for (int i = threadIdx.x; i < ntile; i += 128) {
-        const unsigned k = base + order[i];
-        const GlcmTask e = queue[k];
-        uint8_t w[27];
-        glcm_task_window(lev, P, e.vi, true, w);
-#if GF_LZ_SMEM
-        res[k] = glcm_fast_solve<2>(w, 1, T, e.slot, e.cls, lz_scratch + threadIdx.x, 128);
-#else
-        res[k] = glcm_fast_solve_task(w, 1, T, e.slot);      // per-thread local scratch
-#endif
-      }
-    } else {
-      // dense solves: one template size at a time, block-uniform (idle threads run on an empty window), so the
-      // barriers inside glcm_small_solve keep the warps on the same code (ncu: 8-10 no_instruction stall cycles
-      // per issue with free-running warps -- these bodies are 2-10 k straight-line instructions)
-      if (KIND == 0) {
-        solve_group<4>(lev, P, T, queue, res, order, base, 0, bucket[2]);
-        solve_group<6>(lev, P, T, queue, res, order, base, bucket[2], bucket[4]);
-        solve_group<8>(lev, P, T, queue, res, order, base, bucket[4], bucket[6]);
-      } else {
-        solve_group<10>(lev, P, T, queue, res, order, base, 0, bucket[8]);
-        solve_group<12>(lev, P, T, queue, res, order, base, bucket[8], bucket[GF_DENSE_MAX_CLS]);
-      }
-    }
-    __syncthreads();
-  }
-}
 
 __global__ void __launch_bounds__(256)
 glcm_fast_finish_kernel(const __grid_constant__ VoxParams P, const GlcmTask* __restrict__ queue,
