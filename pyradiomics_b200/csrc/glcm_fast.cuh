@@ -26,7 +26,7 @@ using std::min;
 #define RB_POPC(x) __builtin_popcount((unsigned)(x))
 #endif
 
-#if defined(__CUDA_ARCH__) && defined(RB_GLCM_BLOCK_SYNC)
+#if (defined(__CUDA_ARCH__) || defined(RB_EMULATE_BLOCK)) && defined(RB_GLCM_BLOCK_SYNC)
 #define RB_ANGLE_SYNC() __syncthreads()
 #else
 #define RB_ANGLE_SYNC() ((void)0)

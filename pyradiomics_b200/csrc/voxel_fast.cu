@@ -9,7 +9,7 @@
 #include "common.cuh"
 #define RB_GLCM_BLOCK_SYNC 1   // phase A is called by all threads of a block, uniformly
 #include "glcm_fast.cuh"
-#include "glcm_solve_kernel.cuh"
+#include "glcm_kernels.cuh"
 #include "glrlm_fast.cuh"
 #include "small_fast.cuh"
 #include "host_common.hpp"
@@ -19,93 +19,6 @@ namespace rb {
 constexpr int GF_THREADS = 128;
 
 
-template <int MINB, int NT>
-__global__ void __launch_bounds__(NT, MINB)
-glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ centers,
-                 const __grid_constant__ VoxParams P, const GlcmFastTables* __restrict__ Tg,
-                 double* __restrict__ out, long long fstride, int z0, int z1, int out_z0,
-                 GlcmTask* __restrict__ queue, unsigned* __restrict__ qcount) {
-  __shared__ GlcmFastTables T;
-  __shared__ uint8_t wbuf[27 * NT];
-  __shared__ uint32_t eqbuf[27 * NT];
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(Tg);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
-    for (int i = threadIdx.x; i < (int)(sizeof(GlcmFastTables) / 4); i += NT) dst[i] = src[i];
-  }
-  __syncthreads();
-  const int tid = threadIdx.x;
-  const long long plane = (long long)P.Y * P.X;
-  const long long total = (long long)(z1 - z0) * plane;
-  const long long ntiles = (total + NT - 1) / NT;
-  // block-uniform tile loop: every thread runs phase A (on an all-zero window when its voxel is
-  // not a centre / past the end) so the per-angle barriers inside are reached by the whole block
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long t = tile * NT + tid;
-    const bool live = t < total;
-    const int z = z0 + (int)((live ? t : 0) / plane);
-    const int rem = (int)((live ? t : 0) % plane);
-    const int y = rem / P.X, x = rem % P.X;
-    const long long vi = (long long)z * P.sz + (long long)y * P.sy + x;
-    const long long oi = (long long)(z - out_z0) * plane + rem;
-    const bool is_center = live && (centers ? centers[(long long)z * plane + rem] != 0 : lev[vi] != 0);
-    uint8_t* w = &wbuf[tid];
-#pragma unroll
-    for (int dz = -1; dz <= 1; dz++)
-#pragma unroll
-      for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-        for (int dx = -1; dx <= 1; dx++) {
-          const int zz = z + dz, yy = y + dy, xx = x + dx;
-          const bool in = is_center && zz >= 0 && zz < P.Z && yy >= 0 && yy < P.Y && xx >= 0 && xx < P.X;
-          w[((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1)) * NT] =
-              in ? lev[vi + (long long)dz * P.sz + (long long)dy * P.sy + dx] : (uint8_t)0;
-        }
-    double f[GLCM_NF];
-    int n_ok = 0;
-    unsigned long long tcls = 0;
-    const uint32_t tasks = glcm_fast_voxel_phaseA(w, NT, &eqbuf[tid], NT, T, P, f, &n_ok, &tcls);
-    if (!live) continue;
-    if (!is_center) {
-#pragma unroll
-      for (int k = 0; k < GLCM_NF; k++) out[k * fstride + oi] = P.init_value;
-      continue;
-    }
-#pragma unroll
-    for (int k = 0; k < GLCM_NF; k++) out[k * fstride + oi] = f[k];
-    if (tasks) {
-      const int k = __popc(tasks);
-      unsigned q = atomicAdd(qcount, (unsigned)k);
-      bool first = true;
-      for (uint32_t m = tasks; m; m &= m - 1, q++) {
-        GlcmTask e;
-        e.vi = vi; e.slot = (uint8_t)(__ffs((int)m) - 1); e.n_ok = (uint8_t)n_ok; e.count = first ? (uint8_t)k : 0;
-        e.cls = (uint8_t)(tcls >> (GF_CLS_BITS * e.slot) & (GF_NCLS - 1)); e.unused = 0.f;
-        queue[q] = e;
-        first = false;
-      }
-    }
-  }
-}
-
-
-__global__ void __launch_bounds__(256)
-glcm_fast_finish_kernel(const __grid_constant__ VoxParams P, const GlcmTask* __restrict__ queue,
-                        const unsigned* __restrict__ qcount, const double* __restrict__ res,
-                        double* __restrict__ mcc_map /* out + G_MCC*fstride */, int out_z0) {
-  const unsigned n = *qcount;
-  const long long plane = (long long)P.Y * P.X;
-  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const GlcmTask e = queue[k];
-    if (!e.count) continue;
-    double add = 0;
-    for (int j = 0; j < e.count; j++) add += res[k + j];
-    const int z = (int)(e.vi / P.sz);
-    const long long oi = e.vi - (long long)out_z0 * plane;   // contiguous volume: vi = z*plane + rem
-    (void)z;
-    mcc_map[oi] += add / e.n_ok;
-  }
-}
 
 // device-resident table cache, one per (device, Ng)
 static const GlcmFastTables* glcm_fast_tables_dev(int Ng) {

@@ -1,5 +1,5 @@
 // TEST-ONLY: the CUDA execution model of ONE thread block on the CPU, to run the text of
-// pyradiomics_b200/csrc/glcm_solve_kernel.cuh (tile counting sort, size groups, block-uniform dense solves
+// pyradiomics_b200/csrc/glcm_kernels.cuh (tile counting sort, size groups, block-uniform dense solves
 // with barriers, optional shared-memory Lanczos scratch) without a GPU: one std::thread per CUDA
 // thread, __syncthreads() = pthread barrier, __shared__ = static storage (blocks run one at a time),
 // atomics = GCC atomics.  Built with -fsanitize=thread the same run is a data-race check of the
@@ -39,11 +39,15 @@ static inline int __syncthreads_or(int p) {
   return r;
 }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+#define RB_GLCM_BLOCK_SYNC 1
 static float* g_dyn_shared = nullptr;
 #define RB_DYN_SHARED(type, name) type* name = (type*)g_dyn_shared
 
 #include "../../pyradiomics_b200/csrc/host_common.hpp"
-#include "../../pyradiomics_b200/csrc/glcm_solve_kernel.cuh"
+#include "../../pyradiomics_b200/csrc/glcm_kernels.cuh"
 
 using namespace rb;
 
@@ -110,4 +114,54 @@ extern "C" int emul_solve_kernels(const uint8_t* lev, int Z, int Y, int X, int N
   run_kind<2>(lev, P, T, q.data(), n, res_kernel, nblocks);
   delete T;
   return (int)n;
+}
+
+
+// one emulated launch: `nblocks` blocks of `nthreads` threads, run one block after another
+template <class F>
+static void emu_launch(int nblocks, int nthreads, F body) {
+  blockDim = {(unsigned)nthreads, 1, 1};
+  gridDim = {(unsigned)nblocks, 1, 1};
+  for (int b = 0; b < nblocks; b++) {
+    blockIdx = {(unsigned)b, 0, 0};
+    pthread_barrier_init(&g_barrier, nullptr, nthreads);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < (unsigned)nthreads; t++)
+      th.emplace_back([=]() { threadIdx = {t, 0, 0}; body(); });
+    for (auto& x : th) x.join();
+    pthread_barrier_destroy(&g_barrier);
+  }
+}
+
+// The whole fused GLCM path of glcm_fast_launch on the CPU: phase A (256-thread blocks, per-angle barriers, queue
+// reservation by atomics), the three solve kernels, the finish kernel; planes [0, Z) in chunks of `zchunk`.
+// out: [24][Z][Y][X] float64.  Returns the total number of eigen-tasks.
+extern "C" long long emul_glcm_pipeline(const uint8_t* lev, int Z, int Y, int X, int Ng, int zchunk, double* out) {
+  VoxSettings s;
+  memset(&s, 0, sizeof(s));
+  s.Ng = Ng; s.n_roi_levels = Ng; s.kernelRadius = 1; s.ndist = 1; s.distances[0] = 1; s.symmetricalGLCM = 1;
+  VoxParams P;
+  if (fill_vox_params(C_GLCM, Z, Y, X, s, P)) return -1;
+  GlcmFastTables* T = new GlcmFastTables;
+  glcm_fast_build_tables(*T, Ng);
+  const long long plane = (long long)Y * X, fstride = (long long)Z * plane;
+  std::vector<GlcmTask> q((size_t)zchunk * plane * GF_NA);
+  std::vector<double> res(q.size());
+  std::vector<float> dyn((size_t)GF_LZ_SCRATCH * 128, 1e30f);
+  g_dyn_shared = dyn.data();
+  long long total_tasks = 0;
+  for (int za = 0; za < Z; za += zchunk) {
+    const int zb = za + zchunk < Z ? za + zchunk : Z;
+    unsigned count = 0;
+    GlcmTask* qp = q.data(); double* rp = res.data(); unsigned* cp = &count;
+    emu_launch(3, 256, [=]() { glcm_fast_kernel<1, 256>(lev, nullptr, P, T, out, fstride, za, zb, 0, qp, cp); });
+    for (unsigned k = 0; k < count; k++) res[k] = -12345.0;
+    emu_launch(2, 128, [=]() { glcm_fast_solve_kernel<0>(lev, P, T, qp, cp, rp); });
+    emu_launch(2, 128, [=]() { glcm_fast_solve_kernel<1>(lev, P, T, qp, cp, rp); });
+    emu_launch(2, 128, [=]() { glcm_fast_solve_kernel<2>(lev, P, T, qp, cp, rp); });
+    emu_launch(2, 256, [=]() { glcm_fast_finish_kernel(P, qp, cp, rp, out + (long long)G_MCC * fstride, 0); });
+    total_tasks += count;
+  }
+  delete T;
+  return total_tasks;
 }

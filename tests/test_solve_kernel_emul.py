@@ -1,5 +1,5 @@
 """The eigen-task kernels' ORCHESTRATION on the CPU box: tests/host_emul/solve_kernel_emul.cpp runs the text of
-csrc/glcm_solve_kernel.cuh with one std::thread per CUDA thread (barriers as barriers, shared memory as static
+csrc/glcm_kernels.cuh with one std::thread per CUDA thread (barriers as barriers, shared memory as static
 storage): the tile counting sort, the size groups, the block-uniform dense solves with their barriers and both scratch
 variants of the sparse solver must hand every queued task to exactly one solver and reproduce the direct solve."""
 import ctypes as C
@@ -37,3 +37,29 @@ def test_emulated_solve_kernels_process_every_task_once(tag, defs, kind, n):
     assert np.array_equal(rk, rd)                       # same code, same inputs: bit-identical to the direct solve
     hist = np.bincount(cls, minlength=16)
     assert hist[:7].sum() and hist[7:11].sum() and hist[11:].sum()      # all three kernels had work
+
+
+@pytest.mark.parametrize("kind,n", [("smooth", 12), ("uniform", 13)])
+def test_emulated_glcm_pipeline_equals_per_voxel_math(kind, n):
+    """phase A kernel (per-angle barriers, atomic queue reservation, non-centre voxels) -> three solve kernels -> finish
+    kernel, in plane chunks like glcm_fast_launch, against the single-thread composition of the same math
+    (emul_glcm_fast, itself pinned on the reference's voxel-mode maps in test_host_emul.py)"""
+    from pyradiomics_b200 import _lib
+    pipe = _build("local", [])
+    pipe.emul_glcm_pipeline.restype = C.c_longlong
+    so = os.path.join(HERE, "host_emul", "libemul.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", so, os.path.join(HERE, "host_emul", "emul.cpp")])
+    emul = C.CDLL(so)
+    lev = np.ascontiguousarray(bench.synth_volume(40, kind)[:n, :n, :n].astype(np.uint8))
+    if kind == "smooth":
+        lev[3:6, 2:9, 5] = 0                      # holes: voxels that are not centres, windows with missing pairs
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    out = np.zeros((24, n, n, n))
+    ntasks = pipe.emul_glcm_pipeline(p(lev), n, n, n, 32, 5, p(out))           # 3 plane chunks
+    assert ntasks > 1000
+    ref = np.zeros((24, n, n, n))
+    s = _lib.make_settings(32, 32)
+    lev16 = lev.astype(np.uint16)
+    assert emul.emul_glcm_fast(p(lev16), n, n, n, C.byref(s), None, p(ref)) == 0
+    for k, name in enumerate(_lib.feature_names("glcm")):
+        assert np.array_equal(out[k], ref[k], equal_nan=True), name
