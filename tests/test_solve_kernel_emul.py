@@ -14,11 +14,17 @@ import bench
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+_LIBS = {}
+
+
 def _build(tag, defs):
+    if tag in _LIBS:                       # never overwrite a library this process has loaded
+        return _LIBS[tag]
     so = os.path.join(HERE, "host_emul", f"libsolve_emul_{tag}.so")
     src = os.path.join(HERE, "host_emul", "solve_kernel_emul.cpp")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", "-Wno-unknown-pragmas", *defs, "-shared", "-fPIC", "-o", so, src])
-    return C.CDLL(so)
+    _LIBS[tag] = C.CDLL(so)
+    return _LIBS[tag]
 
 
 @pytest.mark.parametrize("tag,defs", [("local", []), ("smem", ["-DGF_LZ_SMEM=1"])])
@@ -47,9 +53,11 @@ def test_emulated_glcm_pipeline_equals_per_voxel_math(kind, n):
     from pyradiomics_b200 import _lib
     pipe = _build("local", [])
     pipe.emul_glcm_pipeline.restype = C.c_longlong
-    so = os.path.join(HERE, "host_emul", "libemul.so")
-    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", so, os.path.join(HERE, "host_emul", "emul.cpp")])
-    emul = C.CDLL(so)
+    so = os.path.join(HERE, "host_emul", "libemul_pipe.so")          # own copy: test_host_emul.py rebuilds libemul.so
+    if "emul" not in _LIBS:
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", so, os.path.join(HERE, "host_emul", "emul.cpp")])
+        _LIBS["emul"] = C.CDLL(so)
+    emul = _LIBS["emul"]
     lev = np.ascontiguousarray(bench.synth_volume(40, kind)[:n, :n, :n].astype(np.uint8))
     if kind == "smooth":
         lev[3:6, 2:9, 5] = 0                      # holes: voxels that are not centres, windows with missing pairs
