@@ -87,6 +87,7 @@ extern "C" int emul_solve_kernels(const uint8_t* lev, int Z, int Y, int X, int N
   GlcmSolveTables ST;
   glcm_solve_tables_from(*T, ST);
   std::vector<GlcmTask> q;
+  pthread_barrier_init(&g_barrier, nullptr, 1);       // phase A is called from this single thread: its barriers are 1-party
   for (int z = 0; z < Z; z++) for (int y = 0; y < Y; y++) for (int x = 0; x < X; x++) {
     const long long vi = ((long long)z * Y + y) * X + x;
     if (!lev[vi]) continue;
@@ -107,6 +108,7 @@ extern "C" int emul_solve_kernels(const uint8_t* lev, int Z, int Y, int X, int N
       }
     }
   }
+  pthread_barrier_destroy(&g_barrier);
   const unsigned n = (unsigned)q.size();
   for (unsigned k = 0; k < n; k++) res_kernel[k] = -12345.0;      // a task no kernel picks up stays visible
   run_kind<0>(lev, P, T, q.data(), n, res_kernel, nblocks);
