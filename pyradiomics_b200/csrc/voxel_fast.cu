@@ -66,6 +66,7 @@ static GlcmQueue* glcm_queue(cudaStream_t st, size_t need) {
   return &Q;
 }
 
+#if !GF_LZ_SMEM
 // EXPERIMENTAL, off unless B200_GLCM_OVERLAP=1 (prepared at the end of round 1, not yet run on hardware):
 // phase A of plane chunk i+1 on the caller's stream while the eigen-solves + finish of chunk i run on an auxiliary
 // stream, with two task queues.  Phase A is register-bound (one 256-thread CTA fills an SM's register file) and the
@@ -130,6 +131,7 @@ static int glcm_fast_launch_overlap(const uint8_t* lev, const uint8_t* centers, 
   for (int b = 0; b < 2 && b < i; b++) RB_CUDA(cudaStreamWaitEvent(st, O->solved[b], 0));   // the caller's stream sees every MCC map
   return RB_OK;
 }
+#endif
 
 int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P, double* out, long long fstride,
                      int z0, int z1, int out_z0, cudaStream_t st) {
