@@ -115,7 +115,7 @@ glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ 
     for (int j = 0; j < TILE / 128; j++) {
       const unsigned k = base + j * 128 + threadIdx.x;
       mycls[j] = k < n ? queue[k].cls : GF_NCLS;
-      if (mycls[j] >= SolveKind<KIND>::lo && mycls[j] <= SolveKind<KIND>::hi) atomicAdd(&bucket[mycls[j]], 1);
+      if ((int)mycls[j] >= SolveKind<KIND>::lo && (int)mycls[j] <= SolveKind<KIND>::hi) atomicAdd(&bucket[mycls[j]], 1);
     }
     __syncthreads();
     int start = 0, ntile = 0;            // exclusive prefix of this thread's bucket (threads < GF_NCLS)
@@ -130,7 +130,7 @@ glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ 
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < TILE / 128; j++)
-      if (mycls[j] >= SolveKind<KIND>::lo && mycls[j] <= SolveKind<KIND>::hi)
+      if ((int)mycls[j] >= SolveKind<KIND>::lo && (int)mycls[j] <= SolveKind<KIND>::hi)
         order[atomicAdd(&bucket[mycls[j]], 1)] = (uint16_t)(j * 128 + threadIdx.x);
     __syncthreads();
     if (KIND == 2) {
