@@ -100,7 +100,7 @@ glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ 
   if (threadIdx.x == 0) glcm_solve_tables_from(*Tg, T);
   __syncthreads();
   const unsigned n = *qcount;
-  // Tiles of 8 x 128 consecutive tasks are counting-sorted by size class in shared memory, so the
+  // Tiles of GF_SOLVE_TILE (2048) consecutive tasks are counting-sorted by size class in shared memory, so the
   // lanes of a warp run solves of the same size (ncu: 11-14 of 32 lanes active otherwise).
   constexpr int TILE = GF_SOLVE_TILE;
   __shared__ uint16_t order[TILE];
