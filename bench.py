@@ -1,15 +1,23 @@
 #!/usr/bin/env python
-"""bench.py -- voxels/s of full-texture-suite voxel-based extraction (BASELINE.json metric).
+"""bench.py -- voxels/s of full-texture-suite voxel-based extraction (BASELINE.json metric, config 3).
 
-A "step" is one pass of the hot path over the whole synthetic volume: GLCM + GLRLM + GLSZM + GLDM
-+ NGTDM fused kernels -> 75 float64 feature maps (reference dtypes), kernelRadius 1, Ng 32.
+A "step" is one pass of the hot path over the whole synthetic 512^3 volume: GLCM + GLRLM + GLSZM + GLDM + NGTDM fused
+kernels -> 75 float64 feature maps (reference dtypes), kernelRadius 1, Ng 32.
   value  : device-resident (levels in HBM -> maps in HBM), CUDA events, max over ranks
-  e2e    : the same through the host-buffer API (pinned int32 image + mask in, 75 float64 maps out,
-           H2D/D2H inside the timed region)
-  N > 1  : the volume is split into z-slabs, one per GPU ("strong" scaling); every step exchanges
-           the halo planes with NCCL send/recv and all-reduces the GLCM alive-angle mask
-  --impl reference : the reference's own CPU path (compiled `_cmatrices` from oracle/_ref for the
-           matrices + the numpy feature port) on the host cores, bounded voxel sample per step.
+  e2e    : the same through the reference-facing PLUGIN call with HOST buffers: raw int16 image + mask ->
+           Radiomics{GLCM,GLRLM,GLSZM,GLDM,NGTDM}(image, mask, voxelBased=True, binWidth=25).execute() -> 75 float64
+           host maps (H2D, discretisation, kernels, D2H inside the timed region)
+  N > 1  : the volume is split into z-slabs, one per GPU ("strong" scaling); the device-timed step exchanges the halo
+           planes with NCCL send/recv and all-reduces the GLCM alive-angle mask; the e2e step hands every rank the whole
+           host image (bin edges / gray levels of the whole ROI) and each rank returns its slab of the maps
+  parity_sample : OUTSIDE the timed region, >= 20 000 random centre voxels (a quarter of them on the volume's faces, edges
+           and corners) of the produced maps against the CPU oracle (oracle/: the compiled reference `_cmatrices` +
+           the numpy feature restatement) at the north-star tolerance 1e-5; `deterministic`: the step is run twice more
+           and every map compared bit for bit
+  secondary : the smooth volume (same metric), config 2 (GLCM-only 256^3), config 4 (wavelet + LoG -> bin -> suite,
+           12 images at 512^3) and config 5(ii) (batch of 64 independent 256^3 cases, segment-based suite, sharded by case)
+  --impl reference : the reference's own CPU path (compiled `_cmatrices` from oracle/_ref for the matrices + the numpy
+           feature restatement) on the host cores, bounded voxel sample per step.
 """
 from __future__ import annotations
 
@@ -28,9 +36,12 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# algorithmic bytes per voxel with the reference dtypes: int32 image + bool mask in, 8 B per map out.
+# (The timed device-resident path reads a 1-byte packed level volume instead of the 5 B: < 1 % of the figure.)
 ALG_BYTES = {"glcm": 5 + 8 * 24, "glrlm": 5 + 8 * 16, "glszm": 5 + 8 * 16, "gldm": 5 + 8 * 14, "ngtdm": 5 + 8 * 5}
 CLASSES = ("glcm", "glrlm", "glszm", "gldm", "ngtdm")
 METRIC = "voxels/s full-texture voxel-based"
+RTOL, ATOL = 1e-5, 1e-9
 
 
 def synth_volume(n, kind):
@@ -44,27 +55,52 @@ def synth_volume(n, kind):
     return (np.digitize(f, q) + 1).astype(np.int32)
 
 
+def raw_from_levels(lev):
+    """what a scanner would hand over: int16 intensities that binWidth=25 discretises back to `lev`"""
+    return ((lev.astype(np.int32) - 1) * 25 + 3).astype(np.int16)
+
+
+def sample_voxels(n, count, seed):
+    """random centre voxels [3, count]; every fourth one is pushed onto a face / edge / corner of the volume"""
+    rng = np.random.default_rng(seed)
+    vox = rng.integers(0, n, (3, count)).astype(np.int32)
+    b = np.arange(count) % 4 == 0
+    for d in range(3):
+        on = b & (rng.random(count) < 0.6)
+        vox[d, on] = np.where(rng.random(int(on.sum())) < 0.5, 0, n - 1)
+    return vox
+
+
 # ----------------------------------------------------------------------------------- CPU arm
 _CPU = {}
+# the CPU arm is the reference's compiled C for the matrices but the numpy RESTATEMENT for the features (the reference's
+# Python feature classes need SimpleITK / pywt, absent here and on the GPU box): labelled "port", the weaker claim
+CPU_ARM_DETAIL = {"reference": "matrices: the unmodified reference _cmatrices compiled from /root/reference (oracle/_ref); "
+                               "features: numpy restatement oracle/features_np.py",
+                  "port": "matrices: C restatement oracle/cmatrices_port.c; features: numpy restatement oracle/features_np.py"}
 
 
 def _cpu_worker(args):
     """full suite (matrices + features) for a list of centre voxels, reference-style dense path"""
     import features_np as F
-    vox, Ng, levels = args
+    vox, Ng, levels, keep = args
     img, msk, cm = _CPU["img"], _CPU["msk"], _CPU["cm"]
     d1 = np.array([1])
     t0 = time.perf_counter()
+    res = {}
     P, _ = cm.calculate_glcm(img, msk, d1, Ng, False, 0, 1, vox)
-    F.glcm_features(F.glcm_matrix(P, levels), levels, Ng)
+    res["glcm"] = F.glcm_features(F.glcm_matrix(P, levels), levels, Ng)
     del P
     P, _ = cm.calculate_glrlm(img, msk, Ng, int(max(img.shape)), False, 0, 1, vox)
-    F.glrlm_features(P, levels)
+    res["glrlm"] = F.glrlm_features(P, levels)
     del P
-    F.glszm_features(cm.calculate_glszm(img, msk, Ng, int(msk.size), False, 0, 1, vox), levels)
-    F.gldm_features(cm.calculate_gldm(img, msk, d1, Ng, 0, False, 0, 1, vox), levels)
-    F.ngtdm_features(cm.calculate_ngtdm(img, msk, d1, Ng, False, 0, 1, vox))
-    return time.perf_counter() - t0
+    res["glszm"] = F.glszm_features(cm.calculate_glszm(img, msk, Ng, int(msk.size), False, 0, 1, vox), levels)
+    res["gldm"] = F.gldm_features(cm.calculate_gldm(img, msk, d1, Ng, 0, False, 0, 1, vox), levels)
+    res["ngtdm"] = F.ngtdm_features(cm.calculate_ngtdm(img, msk, d1, Ng, False, 0, 1, vox))
+    dt = time.perf_counter() - t0
+    if not keep:
+        return dt, None
+    return dt, {c: {k: np.asarray(v, dtype=np.float64) for k, v in r.items()} for c, r in res.items()}
 
 
 def cpu_arm_setup(vol):
@@ -78,20 +114,24 @@ def cpu_arm_setup(vol):
     return kind
 
 
-def cpu_arm_step(vol, workers, per_worker, seed, pool):
-    rng = np.random.default_rng(seed)
+def cpu_arm_step(vol, workers, per_worker, seed, pool, keep=False, batch=96):
+    """returns (voxels/s, seconds, voxels [3,M], {class: {feature: array[M]}} or None)"""
     n = vol.shape[0]
-    vox = rng.integers(0, n, (3, workers * per_worker)).astype(np.int32)
+    vox = sample_voxels(n, workers * per_worker, seed) if keep else np.random.default_rng(seed).integers(
+        0, n, (3, workers * per_worker)).astype(np.int32)
     levels = np.arange(1, 33)
-    jobs = [(np.ascontiguousarray(vox[:, i * per_worker:(i + 1) * per_worker]), 32, levels) for i in range(workers)]
+    jobs = []
+    for i in range(workers):
+        for b0 in range(0, per_worker, batch):          # dense per-voxel matrices: keep the batches small (1.7 MB / voxel for GLRLM)
+            lo, hi = i * per_worker + b0, i * per_worker + min(b0 + batch, per_worker)
+            jobs.append((np.ascontiguousarray(vox[:, lo:hi]), 32, levels, keep))
     t0 = time.perf_counter()
-    if pool is None:
-        for j in jobs:
-            _cpu_worker(j)
-    else:
-        pool.map(_cpu_worker, jobs)
+    out = [_cpu_worker(j) for j in jobs] if pool is None else pool.map(_cpu_worker, jobs, chunksize=1)
     dt = time.perf_counter() - t0
-    return workers * per_worker / dt, dt
+    feats = None
+    if keep:
+        feats = {c: {k: np.concatenate([o[1][c][k] for o in out]) for k in out[0][1][c]} for c in CLASSES}
+    return workers * per_worker / dt, dt, vox, feats
 
 
 def run_reference(args):
@@ -109,7 +149,7 @@ def run_reference(args):
     t0 = time.perf_counter()
     nvox = 0
     for k in range(args.steps):
-        v, dt = cpu_arm_step(vol, cores, per_worker, k, pool)
+        cpu_arm_step(vol, cores, per_worker, k, pool)
         nvox += cores * per_worker
     total = time.perf_counter() - t0
     if pool:
@@ -121,7 +161,9 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": cores,
+                         "kind": "port", "detail": CPU_ARM_DETAIL[kind],
+                         "sample": sample},
         "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -174,99 +216,297 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------- GPU arm
-def run_b200(args):
+class Ctx:
+    """rank / device / process group of this process"""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        assert self.world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={self.world}"
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+def parity_of(outs, z0, vox, feats):
+    """sampled oracle comparison of device maps {class: [F, nz, Y, X]} (planes z0.. of the volume)"""
     import torch
-    import torch.distributed as dist
+    from pyradiomics_b200 import _lib
+    nz = next(iter(outs.values())).shape[1]
+    sel = (vox[0] >= z0) & (vox[0] < z0 + nz)
+    v = torch.from_numpy(vox[:, sel].astype(np.int64)).to(next(iter(outs.values())).device)
+    n_fail, max_rel, worst, max_abs_small, nan_mismatch = 0, 0.0, None, 0.0, 0
+    for c in outs:
+        got = outs[c][:, v[0] - z0, v[1], v[2]].cpu().numpy()
+        for k, name in enumerate(_lib.feature_names(c)):
+            ref, g = feats[c][name][sel], got[k]
+            nan_mismatch += int((np.isnan(ref) != np.isnan(g)).sum())
+            ok = np.isclose(g, ref, rtol=RTOL, atol=ATOL, equal_nan=True)
+            n_fail += int((~ok).sum())
+            with np.errstate(invalid="ignore", divide="ignore"):
+                d = np.abs(g - ref)
+                big = np.abs(ref) > 1e-6
+                if big.any():
+                    r = float(np.nanmax(np.where(big, d / np.abs(ref), 0.0)))
+                    if r > max_rel:
+                        max_rel, worst = r, f"{c}.{name}"
+                if (~big).any():
+                    max_abs_small = max(max_abs_small, float(np.nanmax(np.where(~big, d, 0.0))))
+    return {"n": int(sel.sum()), "features": sum(len(feats[c]) for c in outs), "max_rel": max_rel, "worst_feature": worst,
+            "max_abs_where_ref_below_1e-6": max_abs_small, "n_outside_tolerance": n_fail, "nan_mismatch": nan_mismatch,
+            "rtol": RTOL, "atol": ATOL, "ok": n_fail == 0 and nan_mismatch == 0,
+            "oracle": "oracle/_ref compiled reference _cmatrices + oracle/features_np.py"}
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
-    vol = synth_volume(args.size, args.kind)
 
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # before CUDA is initialised in this process (fork-safe)
-        import multiprocessing as mp
-        kind = cpu_arm_setup(vol)
-        cores = min(os.cpu_count() or 1, args.cpu_workers)
-        pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
-        cpu_arm_step(vol, cores, 8, 99, pool)
-        v, dt = cpu_arm_step(vol, cores, args.cpu_voxels_per_worker, 0, pool)
-        if pool:
-            pool.close()
-        cpu_baseline = {"value": v, "unit": "voxels/s", "cores": cores, "kind": kind,
-                        "sample": f"{cores * args.cpu_voxels_per_worker} random centre voxels of the same {args.size}^3 "
-                                  f"volume, full suite matrices+features, {dt:.1f} s wall"}
-
+def measure_suite(ctx, vol, steps, warmup, classes=CLASSES, oracle=None, check_determinism=True, sample_clocks=False):
+    """device-resident timing of the fused kernels over `vol` (levels), z-slabs over the ranks"""
+    import torch
     from pyradiomics_b200 import _lib, distributed as D, voxel
-
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    Z = args.size
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    Z = vol.shape[0]
     z0, z1 = D.slab_range(Z, rank, world)
     r = 1
     settings = _lib.make_settings(32, 32)
     own = torch.from_numpy(vol[z0:z1].astype(np.uint8)).to(dev)
     slab = D.SlabHalo(own, r, rank, world)
     nz = z1 - z0
-    outs = {c: torch.empty((_lib.lib().rb_num_features(_lib.CLASS_ID[c]), nz, Z, Z), dtype=torch.float64, device=dev)
-            for c in CLASSES}
-    ev = {c: [] for c in CLASSES}
-    launches = 0
-    zchunk = max(1, (48 << 20) // (Z * Z * 13))
+    outs = {c: torch.empty((_lib.lib().rb_num_features(_lib.CLASS_ID[c]), nz) + vol.shape[1:], dtype=torch.float64, device=dev)
+            for c in classes}
+    ev = {c: [] for c in classes}
+    launches = [0]
+    zchunk = max(1, (48 << 20) // (vol.shape[1] * vol.shape[2] * 13))
     glcm_chunks = -(-nz // zchunk)
 
     def step(record):
-        nonlocal launches
         slab.exchange()
         buf = slab.buf
-        alive = voxel.glcm_alive_angles(buf, settings)
-        alive = D.allreduce_alive(alive, dev)
-        launches += 1                                  # glcm_alive_kernel
-        for c in CLASSES:
+        alive = None
+        if "glcm" in classes:
+            alive = D.allreduce_alive(voxel.glcm_alive_angles(buf, settings), dev)
+            launches[0] += 1                                  # glcm_alive_kernel
+        for c in classes:
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             voxel.voxel_features(c, buf, settings, z0=r, z1=r + nz, out=outs[c], out_z0=r, alive=alive)
-            # GLCM = (features, eigen-solve, finish) kernels per plane chunk of the task queue
-            launches += 5 * glcm_chunks if c == "glcm" else 1   # per plane chunk: phase A, 3 eigen-solve kernels, finish
+            launches[0] += 5 * glcm_chunks if c == "glcm" else 1   # per plane chunk: phase A, 3 eigen-solve kernels, finish
             if record:
                 e1.record()
                 ev[c].append((e0, e1))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step(False)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local) if (sample_clocks and rank == 0) else None
+    if sampler:
         sampler.start()
-    launches = 0
+    launches[0] = 0
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    ctx.barrier()
     s0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(True)
     s1.record()
-    barrier()
-    ms = s0.elapsed_time(s1)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    per_class_ms = {c: float(np.mean([a.elapsed_time(b) for a, b in ev[c]])) for c in CLASSES}
-    nvox_total = Z ** 3
-    value = nvox_total * args.steps / (ms * 1e-3)
+    ctx.barrier()
+    ms = ctx.max_over_ranks(s0.elapsed_time(s1))
+    clocks = sampler.stop() if sampler else None
+    per_class_ms = {c: float(np.mean([a.elapsed_time(b) for a, b in ev[c]])) for c in classes}
+    res = {"value": float(np.prod(vol.shape)) * steps / (ms * 1e-3), "ms_per_step": ms / steps, "per_class_ms": per_class_ms,
+           "launches": launches[0], "clocks": clocks, "nz": nz}
+    # ---- outside the timed region: bit-reproducibility and the sampled oracle comparison
+    if check_determinism:
+        same = True
+        for c in classes:
+            again = torch.empty_like(outs[c])
+            alive = D.allreduce_alive(voxel.glcm_alive_angles(slab.buf, settings), dev) if c == "glcm" else None
+            voxel.voxel_features(c, slab.buf, settings, z0=r, z1=r + nz, out=again, out_z0=r, alive=alive)
+            torch.cuda.synchronize()
+            same = same and bool(torch.equal(again.view(torch.int64), outs[c].view(torch.int64)))
+            del again
+        res["deterministic"] = bool(ctx.sum_over_ranks(0.0 if same else 1.0) == 0.0)
+    if oracle is not None:
+        res["parity_sample"] = parity_of(outs, z0, oracle[0], oracle[1])
+    del outs
+    torch.cuda.empty_cache()
+    return res
 
-    # roofline of the dominant kernel (longest class kernel), algorithmic bytes / event time
+
+def plugin_e2e(ctx, vol, steps, map_dtype="float64"):
+    """end to end through the reference-facing plugin call, host buffers in and out (see module docstring)"""
+    import torch
+    from pyradiomics_b200 import distributed as D, featureclasses as FC
+    raw = raw_from_levels(vol)
+    mask = np.ones(vol.shape, np.uint8)
+    Z = vol.shape[0]
+    z0, z1 = D.slab_range(Z, ctx.rank, ctx.world)
+    kw = dict(voxelBased=True, binWidth=25, b200_map_dtype=map_dtype)
+    if ctx.world > 1:
+        kw["b200_zrange"] = (z0, z1)
+
+    def one():
+        FC.clear_device_cache()                    # every step pays the H2D + discretisation of its image
+        maps = {}
+        for c in ("gldm", "glszm", "glrlm", "ngtdm", "glcm"):
+            maps[c] = FC.FEATURE_CLASSES[c](raw, mask, **kw).execute()
+        return maps
+
+    m = one()                                        # warm-up: faults the page-locked blocks in, builds the tables
+    nmaps = sum(len(v) for v in m.values())
+    probe = float(np.asarray(next(iter(m["glcm"].values())).array).ravel()[0])
+    del m
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m = one()
+        del m
+    torch.cuda.synchronize()
+    dt = ctx.max_over_ranks((time.perf_counter() - t0) / steps)
+    esz = 8 if map_dtype == "float64" else 4
+    d2h = ctx.sum_over_ranks(float(nmaps * (z1 - z0) * vol.shape[1] * vol.shape[2] * esz))
+    h2d = ctx.sum_over_ranks(float(raw.nbytes + mask.nbytes))
+    return {"value": float(np.prod(vol.shape)) / dt, "unit": "voxels/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": steps, "maps": nmaps, "map_dtype": map_dtype,
+            "d2h_gb_per_s_per_rank": d2h / ctx.world / dt / 1e9, "first_value_probe": probe,
+            "api": "pyradiomics_b200.featureclasses.Radiomics{GLCM,GLRLM,GLSZM,GLDM,NGTDM}(raw int16 image, mask, voxelBased=True, "
+                   "binWidth=25).execute(): H2D, discretisation once per image, fused kernels, chunked D2H into page-locked maps; "
+                   "max over ranks"}
+
+
+def secondary_config2(ctx, kinds=("uniform", "smooth")):
+    """BASELINE.json config 2: GLCM feature maps only, 256^3"""
+    out = {}
+    for kind in kinds:
+        vol = synth_volume(256, kind)
+        r = measure_suite(ctx, vol, 5, 3, classes=("glcm",), check_determinism=False)
+        out[kind] = {"value": r["value"], "unit": "voxels/s", "ms_per_step": r["ms_per_step"],
+                     "algorithmic_GBps": ALG_BYTES["glcm"] * r["value"] / 1e9}
+    return {"workload": "GLCM-only voxel-based feature maps, synthetic 256^3 Ng=32 kernelRadius=1, 24 float64 maps", **out}
+
+
+def secondary_config4(ctx, n):
+    """BASELINE.json config 4: wavelet (8 sub-bands) + LoG (sigma 1,2,3) + original -> binWidth 25 -> full suite, one GPU"""
+    import torch
+    from pyradiomics_b200 import pipeline as PL
+    g = torch.Generator(device=ctx.dev).manual_seed(0)
+    x = torch.randn((n, n, n), generator=g, device=ctx.dev, dtype=torch.float32)
+    k = torch.tensor([np.exp(-0.5 * (i / 2.0) ** 2) for i in range(-6, 7)], device=ctx.dev)
+    k = (k / k.sum()).to(torch.float32)
+    for ax in range(3):                                  # separable Gaussian smoothing, sigma 2 (SURVEY.md 8d)
+        shape = [1, 1, 1, 1, 1]
+        shape[2 + ax] = 13
+        pad = [0, 0, 0]
+        pad[ax] = 6
+        x = torch.nn.functional.conv3d(x[None, None], k.view(shape), padding=pad)[0, 0]
+    x = ((x - x.min()) / (x.max() - x.min()) * 800.0).to(torch.float64)
+    mask = torch.ones((n, n, n), dtype=torch.uint8, device=ctx.dev)
+    PL.voxel_suite_with_filters(x[:64, :64, :64].contiguous(), mask[:64, :64, :64].contiguous(), binWidth=25)      # warm-up
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    info = PL.voxel_suite_with_filters(x, mask, binWidth=25)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"workload": f"original + wavelet coif1 (8) + LoG sigma 1,2,3 -> binWidth 25 -> full suite, synthetic {n}^3 float volume",
+            "images": len(info), "ms": ms, "value": len(info) * float(n) ** 3 / (ms * 1e-3), "unit": "voxels/s (image-voxels)",
+            "Ng_per_image": {nm: ng for nm, ng, _ in info}, "filter_parity": "unpinned (PyWavelets / SimpleITK absent; DESIGN.md 5)"}
+
+
+def secondary_config5ii(ctx, ncases=64, n=256):
+    """BASELINE.json config 5(ii): batch of independent cases, segment-based full suite, sharded by case, no collective"""
+    import torch
+    from pyradiomics_b200 import featureclasses as FC
+    mine = [k for k in range(ncases) if k % ctx.world == ctx.rank]
+    mask = np.ones((n, n, n), np.uint8)
+
+    def case(k):
+        g = torch.Generator(device=ctx.dev).manual_seed(1000 + k)
+        lev = torch.randint(1, 33, (n, n, n), generator=g, device=ctx.dev, dtype=torch.int16)
+        return ((lev - 1) * 25 + 3).cpu().numpy()
+
+    def run(raw):
+        FC.clear_device_cache()
+        return {c: FC.FEATURE_CLASSES[c](raw, mask, binWidth=25).execute() for c in CLASSES}
+
+    run(case(ncases))                                   # warm-up
+    raws = [case(k) for k in mine]
+    ctx.barrier()
+    t0 = time.perf_counter()
+    nfeat = 0
+    for raw in raws:
+        nfeat = sum(len(v) for v in run(raw).values())
+    torch.cuda.synchronize()
+    dt = ctx.max_over_ranks(time.perf_counter() - t0)
+    return {"workload": f"batch of {ncases} independent synthetic {n}^3 cases, segment-based full suite ({nfeat} features per case), "
+                        f"cases sharded round-robin over {ctx.world} GPU(s), no collective",
+            "cases": ncases, "seconds": dt, "cases_per_s": ncases / dt, "value": ncases * float(n) ** 3 / dt, "unit": "voxels/s",
+            "ms_per_case_per_gpu": 1e3 * dt / max(1, len(mine)),
+            "api": "Radiomics{GLCM,GLRLM,GLSZM,GLDM,NGTDM}(raw int16 image, mask, binWidth=25).execute() per case (host buffers)"}
+
+
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    sys.path.insert(0, ROOT)
+    from pyradiomics_b200 import numa
+    cpus = numa.bind_to_gpu(local) if not args.no_numa_bind else []       # before any page-locked allocation
+    vol = synth_volume(args.size, args.kind)
+    vol_s = synth_volume(args.size, "smooth") if (not args.no_secondary and args.kind == "uniform") else None
+
+    # ---- CPU oracle legs first (fork-safe: CUDA is not initialised yet): cpu_baseline timing + parity samples
+    cpu_baseline, oracle, oracle_s = None, None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import multiprocessing as mp
+        cores = min(os.cpu_count() or 1, args.cpu_workers)
+        per_worker = -(-args.parity_voxels // cores)
+        kind = cpu_arm_setup(vol)
+        pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
+        cpu_arm_step(vol, cores, 8, 99, pool)
+        v, dt, vox, feats = cpu_arm_step(vol, cores, per_worker, 0, pool, keep=True)
+        if pool:
+            pool.close()
+        oracle = (vox, feats)
+        cpu_baseline = {"value": v, "unit": "voxels/s", "cores": cores,
+                        "kind": "port", "detail": CPU_ARM_DETAIL[kind],
+                        "sample": f"{cores * per_worker} random centre voxels (a quarter on faces/edges/corners) of the same "
+                                  f"{args.size}^3 volume, full suite matrices+features, {dt:.1f} s wall; the values double as the parity sample"}
+        if vol_s is not None:
+            cpu_arm_setup(vol_s)
+            pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
+            _, _, vox_s, feats_s = cpu_arm_step(vol_s, cores, per_worker, 1, pool, keep=True)
+            if pool:
+                pool.close()
+            oracle_s = (vox_s, feats_s)
+
+    ctx = Ctx(args)
+    main = measure_suite(ctx, vol, args.steps, args.warmup, oracle=oracle, sample_clocks=True)
+    value, per_class_ms, nz = main["value"], main["per_class_ms"], main["nz"]
+    Z = args.size
+
+    # roofline of the dominant kernel group (longest class), algorithmic bytes / event time
     dom = max(per_class_ms, key=per_class_ms.get)
     peaks = {}
     try:
@@ -282,49 +522,44 @@ def run_b200(args):
             traffic = prof["dram_bytes_per_launch"] * (nz * Z * Z) / prof["voxels"]
     except (OSError, ValueError, KeyError):
         pass
-    roofline = {"bound": "hbm", "kernel": f"{dom} fused voxel kernel", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": f"{dom} fused voxel kernels", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "ms_per_launch": per_class_ms[dom], "per_class_ms": per_class_ms,
-                "suite_frac": 625.0 * value / world / 1e9 / peak,
-                "note": "compute-bound fp64/integer kernel: see DESIGN.md section 'roofline'"}
+                "suite_frac": 625.0 * value / ctx.world / 1e9 / peak,
+                "note": "issue-bound integer / fp64 kernels, not HBM-bound: see DESIGN.md section 4"}
 
-    # ---- e2e through the host-buffer API: every rank takes its slab (+ halo planes) of the HOST
-    # volume, H2D, discretised-level packing, the five fused kernels, D2H of its slab's 75 maps
     e2e = None
+    secondary = {}
     if not args.no_e2e:
-        del outs
-        torch.cuda.empty_cache()
-        h0, h1 = max(z0 - r, 0), min(z1 + r, Z)
-        hx = voxel.HostExtractor((h1 - h0, Z, Z), CLASSES, dev, z0=z0 - h0, z1=z1 - h0)
-        blk = np.ascontiguousarray(vol[h0:h1])
-        msk = np.ones(blk.shape, np.uint8)
-        hx.run(blk, msk, 32, 32)                             # warm-up (also faults the pinned pages in)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            hx.run(blk, msk, 32, 32)
-        torch.cuda.synchronize()
-        dt = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], dtype=torch.float64, device=dev)
-        hb = torch.tensor([hx.h2d_bytes, hx.d2h_bytes], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            dist.all_reduce(hb, op=dist.ReduceOp.SUM)
-        dtv = float(dt.item())
-        e2e = {"value": nvox_total / dtv, "unit": "voxels/s", "h2d_bytes_per_step": int(hb[0].item()),
-               "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": dtv * 1e3, "steps": args.e2e_steps,
-               "api": "pyradiomics_b200.voxel.HostExtractor.run (pinned host buffers per rank, D2H overlapped per class, max over ranks)"}
+        e2e = plugin_e2e(ctx, vol, args.e2e_steps)
+        if not args.no_secondary:
+            f32 = plugin_e2e(ctx, vol, args.e2e_steps, "float32")
+            secondary["e2e_float32_maps"] = {k: f32[k] for k in ("value", "unit", "ms_per_step", "d2h_bytes_per_step", "map_dtype",
+                                                                 "d2h_gb_per_s_per_rank")}
+    if not args.no_secondary:
+        if vol_s is not None:
+            s = measure_suite(ctx, vol_s, 3, 3, oracle=oracle_s)
+            secondary["smooth_volume"] = {
+                "workload": workload_config(argparse.Namespace(size=args.size, kind="smooth", gpus=args.gpus))["workload"],
+                "value": s["value"], "unit": "voxels/s", "ms_per_step": s["ms_per_step"], "per_class_ms": s["per_class_ms"],
+                "deterministic": s.get("deterministic"), "parity_sample": s.get("parity_sample")}
+        secondary["config2_glcm_256"] = secondary_config2(ctx)
+        if world == 1:
+            secondary["config4_filters_suite"] = secondary_config4(ctx, args.size)
+        secondary["config5ii_segment_batch"] = secondary_config5ii(ctx)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "cpu_baseline": cpu_baseline,
+            "clocks": main["clocks"], "e2e": e2e, "gpu_launches": main["launches"], "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "parity_sample": main.get("parity_sample"),
+            "deterministic": main.get("deterministic"), "numa_cpus": len(cpus), "secondary": secondary or None,
         }
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
 
 
 def main():
@@ -338,8 +573,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--cpu-workers", type=int, default=64)
     ap.add_argument("--cpu-voxels-per-worker", type=int, default=96)
+    ap.add_argument("--parity-voxels", type=int, default=20480)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -105,6 +105,18 @@ int rb_voxel_features_dev(int cls, const void *levels_dev, int level_bytes, cons
                           const uint32_t *alive_host, void *out_dev, int out_is_f32,
                           long long out_feature_stride, int out_z0, int *status_dev, void *stream);
 
+/* Output assembly (reference radiomics/base.py:205-209,232-234: the maps a voxel-based class returns are
+ * full-size float64 host arrays).  The fused kernels leave [F][Z][Y][X] maps on the device; these two helpers move a
+ * z-chunk of SEVERAL maps with one strided DMA instead of one copy per map:
+ * rb_memcpy2d_async: `height` rows of `width` bytes, row pitches in bytes; kind 1 = host->device, 2 = device->host,
+ *   3 = device->device (cudaMemcpy2DAsync on `stream`; host memory should be page-locked for a true async copy).
+ * rb_maps_to_f32_dev: rows of `width` float64 elements -> float32 (element pitches), the opt-in compact map type
+ *   (half the PCIe bytes; the tolerance of the path is 1e-5 relative, float32 carries 6e-8). */
+int rb_memcpy2d_async(void *dst, unsigned long long dpitch, const void *src, unsigned long long spitch,
+                      unsigned long long width, unsigned long long height, int kind, void *stream);
+int rb_maps_to_f32_dev(const double *src_dev, long long src_pitch, float *dst_dev, long long dst_pitch,
+                       long long width, long long height, void *stream);
+
 /* Host-buffer convenience (what a ctypes/cgo caller with NumPy-like arrays uses; e2e path):
  * image int32 + mask bytes (nonzero = ROI; levels must already be discretised, 1..Ng) in, float64
  * maps out: maps[f][z][y][x], f < rb_num_features(cls).  Synchronous. */

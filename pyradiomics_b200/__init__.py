@@ -7,3 +7,9 @@ and torch.distributed.  There is no CPU fallback anywhere in the product path.
 from ._lib import B200Error, CLASSES, feature_names, lib  # noqa: F401
 
 __version__ = "0.1.0"
+
+
+def install(radiomics_module=None):
+    """register the B200 feature classes / cMatrices / cShape in an importable pyradiomics (featureclasses.install)"""
+    from .featureclasses import install as _install
+    return _install(radiomics_module)

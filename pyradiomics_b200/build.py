@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200radiomics.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "128",
+    "-Xcompiler", "-fPIC", "-diag-suppress", "128",
 ]
 
 
@@ -33,9 +33,25 @@ def build_variant(name: str, defines: list[str]) -> str:
     (load it with B200_RADIOMICS_LIB=<path>); used to A/B kernel variants inside one GPU session."""
     out = os.path.join(HERE, "variants", f"lib{name}.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    subprocess.check_call([nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out, *sources(), "-lcuda"], cwd=CSRC)
+    _compile_and_link(out, [f"-D{d}" for d in defines], os.path.join(HERE, "variants", f"obj_{name}"))
     return out
+
+
+def _compile_and_link(out: str, extra: list[str], objdir: str, verbose: bool = False) -> None:
+    """one nvcc per .cu in parallel (the translation units are independent: no relocatable device code), then link"""
+    from concurrent.futures import ThreadPoolExecutor
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    os.makedirs(objdir, exist_ok=True)
+    jobs = []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        jobs.append((src, obj, [nvcc, *NVCC_FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []), "-c", src, "-o", obj]))
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        for rc in ex.map(lambda j: subprocess.call(j[2], cwd=CSRC), jobs):
+            if rc:
+                raise RuntimeError("nvcc failed")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out, *[j[1] for j in jobs], "-lcuda"], cwd=CSRC)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -46,8 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if os.path.exists(LIB):
             return LIB
         raise RuntimeError("nvcc not found and libb200radiomics.so is not built")
-    cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB, *sources(), "-lcuda"]
-    subprocess.check_call(cmd, cwd=CSRC)
+    _compile_and_link(LIB, [], os.path.join(HERE, "build"), verbose)
     return LIB
 
 

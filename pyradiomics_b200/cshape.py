@@ -12,6 +12,16 @@ import numpy as np
 
 from ._lib import check, lib
 
+_fallback = None        # the reference's _cshape module, set by featureclasses.install()
+
+
+def __getattr__(name):
+    """names this module does not implement (calculate_coefficients2D: reference radiomics/src/_cshape.c:33-39,
+    used by radiomics/shape2D.py:99) are served by the reference's own extension when install() found one"""
+    if _fallback is not None and hasattr(_fallback, name):
+        return getattr(_fallback, name)
+    raise AttributeError(f"module 'pyradiomics_b200.cshape' has no attribute {name!r}")
+
 
 def calculate_coefficients(mask, pixelSpacing):
     """(SurfaceArea, Volume, (Maximum2DDiameterSlice, ...Column, ...Row, Maximum3DDiameter))"""

@@ -101,6 +101,15 @@ static VoxSettings to_settings(const rb_voxel_settings* s) {
   return v;
 }
 
+__global__ void maps_to_f32_kernel(const double* __restrict__ src, long long sp, float* __restrict__ dst, long long dp,
+                                   long long width, long long height) {
+  const long long total = width * height;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / width, c = i - r * width;
+    dst[r * dp + c] = (float)src[r * sp + c];
+  }
+}
+
 }  // namespace rb
 
 using namespace rb;
@@ -170,6 +179,26 @@ int rb_voxel_features_dev(int cls, const void* levels_dev, int level_bytes, cons
                              (cudaStream_t)stream);
   return voxel_features_generic(cls, levels_dev, level_bytes, centers_dev, P, (double*)out_dev, out_feature_stride, z0,
                                 z1, out_z0, status_dev, (cudaStream_t)stream);
+}
+
+int rb_memcpy2d_async(void* dst, unsigned long long dpitch, const void* src, unsigned long long spitch,
+                      unsigned long long width, unsigned long long height, int kind, void* stream) {
+  const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (kind < 1 || kind > 3) return fail(RB_ERR_ARG, "rb_memcpy2d_async: kind must be 1, 2 or 3");
+  if (!width || !height) return RB_OK;
+  RB_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, k, (cudaStream_t)stream));
+  return RB_OK;
+}
+
+int rb_maps_to_f32_dev(const double* src_dev, long long src_pitch, float* dst_dev, long long dst_pitch, long long width,
+                       long long height, void* stream) {
+  if (width <= 0 || height <= 0) return RB_OK;
+  const long long total = width * height;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  maps_to_f32_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src_dev, src_pitch, dst_dev, dst_pitch, width, height);
+  RB_LAUNCH_CHECK();
+  return RB_OK;
 }
 
 int rb_voxel_features_host(int cls, const int32_t* image, const uint8_t* mask, int Z, int Y, int X,

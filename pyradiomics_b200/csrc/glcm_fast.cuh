@@ -5,9 +5,10 @@
 //   * co-occurrence multiplicities come from pairwise compares of (|a-b|, a+b) keys instead of a
 //     merged entry list; all "linear in p" features are exact integer sums;
 //   * every log2 is a table lookup (arguments are ratios of small integers);
-//   * MCC: the level graph's connectivity is decided with bitmask propagation; only a connected
-//     graph needs an eigen-solve (Householder tridiagonalisation + Sturm bisection on the symmetric n x n matrix
-//     P/sqrt(px px), n <= 19).
+//   * MCC: the level graph's connectivity and 2-colourability are decided with bitmask propagation; only a
+//     connected, non-bipartite graph needs an eigen-solve of the symmetric n x n matrix P/sqrt(px px), n <= 18:
+//     dense Householder + Laguerre in registers up to 12 levels (glcm_small_solve), a register-resident Lanczos
+//     recurrence above (glcm_lanczos.cuh).
 // __host__ __device__ so tests/host_emul can check the arithmetic on the CPU (test-only).
 #pragma once
 #include "vox_features.cuh"
@@ -37,34 +38,15 @@ namespace rb {
 constexpr int GF_NA = 13;
 constexpr int GF_LOGT = 40;       // log2 table covers 0..2*18+1
 constexpr int GF_KT = 256;        // |a-b| tables
-#ifndef RB_LZ_T
-#define RB_LZ_T float
-#endif
-#ifndef RB_TD_T
-#define RB_TD_T float     // storage of the Lanczos tridiagonal (eigenvalue error <= 1e-7)
-#endif
 #ifndef GF_DENSE_SMALL
 #define GF_DENSE_SMALL 1
 #endif
 #ifndef GF_DENSE_MAX_CLS
 #define GF_DENSE_MAX_CLS 10     // n <= 12 solved densely in registers
 #endif
-#ifndef GF_LOCAL_REORTH
-#define GF_LOCAL_REORTH 1
-#endif
-#ifndef GF_EXTRA_STEPS
-#define GF_EXTRA_STEPS 3     // extra Lanczos steps for tasks that met a small beta (see GF_SMALL_BETA)
-#endif
-#ifndef GF_SMALL_BETA
-#define GF_SMALL_BETA 0.003   // 1e-3 already reproduces the always-extend accuracy (<= 3e-7 over 5e5 windows); 1e-4 does not
-#endif
 #ifndef GF_BREAKDOWN
 #define GF_BREAKDOWN 1e-10
 #endif
-#ifndef GF_LANCZOS_ATTEMPTS
-#define GF_LANCZOS_ATTEMPTS 1
-#endif
-constexpr int GF_BISECT = 27;     // Sturm bisection steps: interval 2/2^27 = 1.5e-8 (tolerance budget 1e-5)
 
 struct GlcmFastTables {
   // per angle (in processing order: 3 axis, 6 face-diagonal, 4 body-diagonal)
@@ -73,15 +55,14 @@ struct GlcmFastTables {
   uint8_t pA[GF_NA][18], pB[GF_NA][18];      // window positions (z*9+y*3+x) of the two pair ends
   double log2t[GF_LOGT];          // log2(c), log2t[0] = 0 (never used with weight)
   double idm[GF_KT], idmn[GF_KT], id[GF_KT], idn[GF_KT], inv[GF_KT];   // by k = |i-j|
-  double lz0[19], lz1[19];        // Lanczos start vectors (see kLanczosStart0/1)
+  double lz0[19];                 // Lanczos start vector (see kLanczosStart0)
   double rsq[GF_LOGT];            // 1 / sqrt(c) for the small integer row sums
 };
 
-// Lanczos start vectors: two fixed tables of unstructured components in [0.25, 1.25) (drawn once
-// from a PRNG; anything "generic" works -- arithmetic progressions and Weyl sequences do NOT, they
-// are exactly deficient for symmetric level graphs).
+// Lanczos start vector: a fixed table of unstructured components in [0.25, 1.25) (drawn once from a
+// PRNG; anything "generic" works -- arithmetic progressions and Weyl sequences do NOT, they are exactly
+// deficient for symmetric level graphs).
 static const double kLanczosStart0[19] = {0.47733602246716966, 0.56675833970975287, 1.047365457332734, 0.92625467075097456, 0.641109550601909, 0.58281392786638453, 0.84830875358718982, 0.43673418560371335, 0.9227560440146213, 1.1918028652699371, 0.49824571462957101, 1.1988811518333182, 0.91723745310037241, 0.34589793559411208, 0.69183966616781278, 1.1364799193275177, 0.9474534998820221, 0.57647286407011211, 0.9839281633300665};
-static const double kLanczosStart1[19] = {0.47013495554548623, 0.33159456954220812, 0.40989560107504752, 0.59010018495470529, 0.71519315370205094, 0.51642102829077097, 1.065776403424807, 0.44329438928949449, 0.37946907617720027, 0.34166475154493592, 0.84856801366491319, 1.1047419043740012, 0.85162124169371312, 1.1819883611359834, 0.97478136109202007, 1.1105513173932924, 1.1793378015753162, 0.79618600908235304, 1.1876729587677568};
 
 // Host-side construction (Ng = max gray level of the ROI, as used by Idmn / Idn).
 inline void glcm_fast_build_tables(GlcmFastTables& T, int Ng) {
@@ -108,7 +89,7 @@ inline void glcm_fast_build_tables(GlcmFastTables& T, int Ng) {
       for (int t = n; t < 18; t++) { T.pA[slot][t] = 0; T.pB[slot][t] = 0; }
       slot++;
     }
-  for (int i = 0; i < 19; i++) { T.lz0[i] = kLanczosStart0[i]; T.lz1[i] = kLanczosStart1[i]; }
+  for (int i = 0; i < 19; i++) T.lz0[i] = kLanczosStart0[i];
   T.log2t[0] = 0; T.rsq[0] = 0;
   for (int c = 1; c < GF_LOGT; c++) { T.log2t[c] = log2((double)c); T.rsq[c] = 1.0 / sqrt((double)c); }
   for (int d = 0; d < GF_KT; d++) {
@@ -121,20 +102,14 @@ inline void glcm_fast_build_tables(GlcmFastTables& T, int Ng) {
   }
 }
 
-// MCC eigen-task: second largest |eigenvalue| of the symmetric matrix M(i,j) = n_ij / sqrt(R_i R_j)
-// (normalised co-occurrence of ONE angle whose level graph is connected; its top eigenpair is
-// (1, sqrt(R/S))).  M has <= NP off-diagonal pairs, so instead of a dense O(n^3) reduction it is
-// tridiagonalised by a Lanczos recurrence with SPARSE mat-vecs, started and kept orthogonal to the
-// known top eigenvector; the extreme eigenvalues of the small tridiagonal are then located by
-// Sturm bisection.  Rebuilds everything from the voxel's 27 window levels (w, stride ws) alone, so
-// any thread can execute any voxel's task.
 // the part of the tables the eigen-solver needs (1.1 KB; the solve kernel keeps only this in shared
 // memory so that the L1 carve-out goes to the per-thread Lanczos state)
 struct GlcmSolveTables {
   uint8_t np[GF_NA];
   uint8_t pA[GF_NA][18], pB[GF_NA][18];
-  double lz0[19], lz1[19];
+  double lz0[19];
   double rsq[GF_LOGT];
+  double rinv[GF_LOGT];           // 1 / c (rinv[0] = 0): row-sum reciprocals of the register Lanczos solver
   // pairs of an angle as bit sets over the 27 window positions: every pair is (p, p + dshift) for a
   // position p in lo_mask
   uint32_t lo_mask[GF_NA];
@@ -149,156 +124,8 @@ RB_HD void glcm_solve_tables_from(const GlcmFastTables& T, GlcmSolveTables& S) {
     S.lo_mask[a] = lo;
     S.dshift[a] = (uint8_t)(T.pA[a][0] < T.pB[a][0] ? T.pB[a][0] - T.pA[a][0] : T.pA[a][0] - T.pB[a][0]);
   }
-  for (int i = 0; i < 19; i++) { S.lz0[i] = T.lz0[i]; S.lz1[i] = T.lz1[i]; }
-  for (int i = 0; i < GF_LOGT; i++) S.rsq[i] = T.rsq[i];
-}
-
-// scr: per-thread float scratch of GF_LZ_SCRATCH elements with element stride st (device: shared
-// memory, [element][thread] so a warp's accesses never conflict; host / generic callers: a local buffer,
-// st = 1).  Shared memory instead of per-thread local arrays: ncu showed 11.6 long-scoreboard stall
-// cycles per issue from local-memory L1 misses (32 warps x ~0.7 KB each do not fit L1).
-constexpr int GF_LZ_SCRATCH = 4 * 19 + 18 + 2 * (19 + GF_EXTRA_STEPS);
-template <class TT>
-RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const TT& T, int s, RB_LZ_T* scr, int st) {
-#define v1(i) scr[(i) * st]
-#define q0(i) scr[(19 + (i)) * st]
-#define q1(i) scr[(38 + (i)) * st]
-#define z(i) scr[(57 + (i)) * st]
-#define ew(i) scr[(76 + (i)) * st]
-  RB_LZ_T* const d = scr + 94 * st;
-  RB_LZ_T* const e = scr + (94 + 19 + GF_EXTRA_STEPS) * st;
-  const int np = T.np[s];
-  const uint8_t* pA = T.pA[s];
-  const uint8_t* pB = T.pB[s];
-  // level nodes (<= 19 for a connected graph with <= 18 edges), R = endpoint multiplicity = row sum
-  // stored in float (halves the per-thread scratch that has to stay in L1); all arithmetic in double
-  uint8_t nodelev[19], ei[18], ej[18];
-  int n = 0, ne = 0;
-  for (int i = 0; i < 19; i++) v1(i) = 0;
-  for (int t = 0; t < np; t++) {
-    const uint8_t a = w[pA[t] * ws], b = w[pB[t] * ws];
-    if (!a || !b) continue;
-    int i = 0, j = 0;
-    for (; i < n; i++) if (nodelev[i] == a) break;
-    if (i == n) { if (n >= 19) return 1.0; nodelev[n++] = a; }
-    for (; j < n; j++) if (nodelev[j] == b) break;
-    if (j == n) { if (n >= 19) return 1.0; nodelev[n++] = b; }
-    ei[ne] = (uint8_t)i; ej[ne] = (uint8_t)j; ne++;
-    v1(i) += 1.0; v1(j) += 1.0;
-  }
-  if (n < 2) return 0.0;
-  {
-    // bipartite (2-colourable, no self-loop) connected graph: eigenvalue -1 -> |.| = 1
-    bool selfloop = false;
-    for (int t = 0; t < ne; t++) selfloop |= ei[t] == ej[t];
-    if (!selfloop) {
-      uint32_t A = 1u, B = 0;            // colour classes as bit sets of node indices
-      for (int sweep = 0; sweep < n; sweep++) {
-        const uint32_t a0 = A, b0 = B;
-        for (int t = 0; t < ne; t++) {
-          const uint32_t bi = 1u << ei[t], bj = 1u << ej[t];
-          if (A & bi) B |= bj;
-          if (B & bi) A |= bj;
-          if (A & bj) B |= bi;
-          if (B & bj) A |= bi;
-        }
-        if (A == a0 && B == b0) break;
-      }
-      if ((A & B) == 0) return 1.0;
-    }
-  }
-  // row sums are small integers (<= 36): 1/sqrt from a table
-  double S = 0, tr = 0;
-  for (int i = 0; i < n; i++) S += v1(i);
-  for (int t = 0; t < ne; t++) {
-    ew(t) = T.rsq[(int)v1(ei[t])] * T.rsq[(int)v1(ej[t])];
-    if (ei[t] == ej[t]) tr += 2.0 * ew(t);      // trace of M
-  }
-  if (n == 2) return fabs(tr - 1.0);          // eigenvalues are 1 and trace - 1
-  const double invS = 1.0 / S;
-  for (int i = 0; i < n; i++) v1(i) = sqrt(v1(i) * invS);
-  // Lanczos from a fixed pseudo-random start vector projected off v1.  If the recurrence breaks
-  // down before n-1 steps the Ritz values found are still exact eigenvalues; with unstructured
-  // start components a breakdown means repeated eigenvalues, not a missed one (60000 random and
-  // structured windows agree with LAPACK to 2e-7 with a single attempt; GF_LANCZOS_ATTEMPTS=2 adds a
-  // second start vector).
-  double best = 0;
-  for (int attempt = 0; attempt < GF_LANCZOS_ATTEMPTS; attempt++) {
-    double dot = 0, nrm = 0;
-    for (int i = 0; i < n; i++) {
-      q1(i) = attempt == 0 ? T.lz0[i] : T.lz1[i];
-      dot += q1(i) * v1(i);
-    }
-    for (int i = 0; i < n; i++) { q1(i) -= dot * v1(i); nrm += q1(i) * q1(i); q0(i) = 0; }
-    nrm = 1.0 / sqrt(nrm);
-    for (int i = 0; i < n; i++) q1(i) *= nrm;
-    double beta = 0;
-    int m = 0;
-    e[(0) * st] = 0;
-    int jmax = n - 2;
-    bool extended = false;
-    for (int j = 0; j <= jmax; j++) {
-      for (int i = 0; i < n; i++) z(i) = 0;
-      for (int t = 0; t < ne; t++) {
-        const int a = ei[t], b = ej[t];
-        z(a) += ew(t) * q1(b);
-        z(b) += ew(t) * q1(a);
-      }
-      double alpha = 0;
-      for (int i = 0; i < n; i++) alpha += q1(i) * z(i);
-      double dv = 0;
-      for (int i = 0; i < n; i++) { z(i) -= alpha * q1(i) + beta * q0(i); dv += z(i) * v1(i); }
-#if GF_LOCAL_REORTH
-      // re-orthogonalise against the deflated vector and the last two Lanczos vectors
-      double c1 = 0, c0 = 0;
-      for (int i = 0; i < n; i++) { z(i) -= dv * v1(i); c1 += z(i) * q1(i); c0 += z(i) * q0(i); }
-      double nb = 0;
-      for (int i = 0; i < n; i++) { z(i) -= c1 * q1(i) + c0 * q0(i); nb += z(i) * z(i); }
-#else
-      // keep the iterate orthogonal to the deflated (known) eigenvector
-      double nb = 0;
-      for (int i = 0; i < n; i++) { const double zi = z(i) - dv * v1(i); z(i) = zi; nb += zi * zi; }
-#endif
-      d[(m) * st] = alpha; m++;
-      nb = sqrt(nb);
-      if (nb < GF_BREAKDOWN) break;             // invariant subspace reached
-      // a small beta amplifies the rounding of the float-stored vectors (orthogonality is lost and
-      // n-1 steps no longer span the space): such tasks run GF_EXTRA_STEPS more steps
-      if (j >= jmax) break;
-      if (nb < GF_SMALL_BETA && !extended && n > 4) { extended = true; jmax += GF_EXTRA_STEPS; }
-      e[(m) * st] = nb; beta = nb;
-      const double inb = 1.0 / nb;
-      for (int i = 0; i < n; i++) { q0(i) = q1(i); q1(i) = z(i) * inb; }
-    }
-    if (m <= 2) {                             // closed forms for 1x1 / 2x2
-      double hi2 = d[(0) * st], lo2 = d[(0) * st];
-      if (m == 2) {
-        const double mid = 0.5 * ((double)d[(0) * st] + d[(1) * st]), hd = 0.5 * ((double)d[(0) * st] - d[(1) * st]), rad = sqrt(hd * hd + (double)e[(1) * st] * e[(1) * st]);
-        hi2 = mid + rad; lo2 = mid - rad;
-      }
-      best = fmax(best, fmax(fabs(hi2), fabs(lo2)));
-      if (m == n - 1) break;
-      continue;
-    }
-    // both extreme eigenvalues of the deflated tridiagonal in one Laguerre loop (the Lanczos betas
-    // are > 1e-10, so T is unreduced: simple eigenvalues)
-    double hi, lo;
-    tridiag_extreme_pair(d, e, m, &hi, &lo, st);
-    best = fmax(best, fmax(fabs(hi), fabs(lo)));
-    if (m == n - 1) break;
-  }
-  return best;
-#undef v1
-#undef q0
-#undef q1
-#undef z
-#undef ew
-}
-// convenience: private scratch (host emulation, generic callers)
-template <class TT>
-RB_HDN double glcm_fast_solve_task(const uint8_t* w, int ws, const TT& T, int s) {
-  RB_LZ_T scr[GF_LZ_SCRATCH];
-  return glcm_fast_solve_task(w, ws, T, s, scr, 1);
+  for (int i = 0; i < 19; i++) S.lz0[i] = T.lz0[i];
+  for (int i = 0; i < GF_LOGT; i++) { S.rsq[i] = T.rsq[i]; S.rinv[i] = i ? 1.0 / (double)i : 0.0; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -492,32 +319,43 @@ RB_HD double glcm_small_solve(const uint8_t* w, int ws, const uint32_t* W7, cons
   return fmax(fabs(hi), fabs(lo));
 }
 
-// eigen-task entry point.  cls = n - 2 (glcm_task_class).  KIND selects the size range one solve kernel
-// handles: 0: n <= 8 and 1: n <= 12 (dense register solves), 2: larger graphs (sparse Lanczos),
-// -1: any (host emulation).
-template <int KIND, class TT>
-RB_HD double glcm_fast_solve(const uint8_t* w, int ws, const TT& T, int s, int cls, RB_LZ_T* scr = nullptr, int st = 1) {
-#if GF_DENSE_SMALL
-  if ((KIND == 0 || KIND == 1 || KIND == -1) && cls <= GF_DENSE_MAX_CLS) {
+}  // namespace rb
+#include "glcm_lanczos.cuh"
+namespace rb {
+
+// large eigen-task (n >= 13 levels) of angle slot s by size class; sm = LZ_NARR*18 doubles of per-thread scratch with
+// element stride st.  Only the three axis angles (slots 0..2, 18 pairs) can carry a connected NON-bipartite graph on
+// 13+ levels: a 12-pair angle reaches 13 levels only as a tree, and 19 levels on 18 pairs is a tree too -- trees are
+// bipartite, eigenvalue -1, MCC term 1 (phase A filters them; answered here as well so the function is total).
+template <class TT>
+RB_HD double glcm_lanczos_solve(const uint8_t* w, int ws, const TT& T, int s, int cls, double* sm, int st) {
+  if (s > 2) return 1.0;
+  int n = 0;
+  double r;
+  if (cls <= 12) r = glcm_lanczos_task<14>(w, ws, T, s, sm, st, &n);
+  else if (cls <= 14) r = glcm_lanczos_task<16>(w, ws, T, s, sm, st, &n);
+  else { r = glcm_lanczos_task<18>(w, ws, T, s, sm, st, &n); if (n == 19) r = 1.0; }
+  return r;
+}
+
+// eigen-task entry point of the single-thread composition (host emulation / generic callers).  cls = n - 2
+// (glcm_task_class).  The device kernels call glcm_small_solve / glcm_lanczos_task directly, one size at a time.
+template <class TT>
+RB_HD double glcm_fast_solve(const uint8_t* w, int ws, const TT& T, int s, int cls) {
+  if (cls <= GF_DENSE_MAX_CLS) {
     uint32_t W7[7];
     glcm_pack_window(w, ws, W7);
     bool ok = false;
-    double r = 0;
-    if (KIND != 1 && cls <= 6) {
-      if (cls <= 2) r = glcm_small_solve<4>(w, ws, W7, T, s, &ok);
-      else if (cls <= 4) r = glcm_small_solve<6>(w, ws, W7, T, s, &ok);
-      else r = glcm_small_solve<8>(w, ws, W7, T, s, &ok);
-    } else if (KIND != 0) {
-      if (cls <= 8) r = glcm_small_solve<10>(w, ws, W7, T, s, &ok);
-      else r = glcm_small_solve<12>(w, ws, W7, T, s, &ok);
-    }
-    if (ok) return r;
-    if (KIND != -1) return NAN;        // cannot happen: cls is the exact node count
+    double r;
+    if (cls <= 2) r = glcm_small_solve<4>(w, ws, W7, T, s, &ok);
+    else if (cls <= 4) r = glcm_small_solve<6>(w, ws, W7, T, s, &ok);
+    else if (cls <= 6) r = glcm_small_solve<8>(w, ws, W7, T, s, &ok);
+    else if (cls <= 8) r = glcm_small_solve<10>(w, ws, W7, T, s, &ok);
+    else r = glcm_small_solve<12>(w, ws, W7, T, s, &ok);
+    return ok ? r : NAN;               // (cannot fail: cls is the exact node count)
   }
-#endif
-  if (KIND == 0 || KIND == 1) return NAN;
-  if (KIND == 2) return glcm_fast_solve_task(w, ws, T, s, scr, st);       // device: shared-memory scratch
-  return glcm_fast_solve_task(w, ws, T, s);
+  double sm[LZ_NARR * 18];
+  return glcm_lanczos_solve(w, ws, T, s, cls, sm, 1);
 }
 
 // size class of an eigen-task (number of level nodes) -- tasks of one class share a warp
@@ -545,6 +383,7 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
   int key1[NP], key2[NP];
   uint32_t valid = 0, EA = 0, EB = 0;
   int n = 0, Ssum = 0, Sab = 0, Sq = 0, Skd = 0;
+  bool selfpair = false;               // a level paired with itself: the level graph has a self-loop
 #pragma unroll
   for (int t = 0; t < NP; t++) {
     const int a = w[pA[t] * ws], b = w[pB[t] * ws];
@@ -555,6 +394,7 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
     if (ok) {
       valid |= 1u << t; EA |= 1u << pA[t]; EB |= 1u << pB[t];
       n++; Ssum += ks; Sab += a * b; Sq += a * a + b * b; Skd += kd;
+      selfpair |= kd == 0;
     }
   }
   const int orig = T.orig[s];
@@ -562,42 +402,32 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
     if (P.alive[orig >> 5] >> (orig & 31) & 1u) acc.ja_nan = true;
     return;
   }
-  // ---- level classes of the pair ends: marginal entropy and the level graph of this angle.
+  // ---- level classes of the pair ends (one visit per class, not per pair end): marginal entropy.
   // R(level) = number of matrix entries in its row = popcount(class & EA) + popcount(class & EB);
-  // sum_levels R log2 R = sum over the 2n pair ends of log2 R(their level).
+  // sum_levels R log2 R feeds HX = HY.
+  const uint32_t U = EA | EB;
   double rl = 0;
-  uint32_t reps = 0, all = 0, comp = 0;
-  uint32_t em[NP];
-#pragma unroll
-  for (int t = 0; t < NP; t++) {
-    em[t] = 0;
-    if (valid >> t & 1u) {
-      const uint32_t ea = eq[pA[t] * es], eb = eq[pB[t] * es];
-      rl += T.log2t[RB_POPC(ea & EA) + RB_POPC(ea & EB)] + T.log2t[RB_POPC(eb & EA) + RB_POPC(eb & EB)];
-      reps |= (ea & (0u - ea)) | (eb & (0u - eb));          // lowest position of each class
-      em[t] = ea | eb;
-      all |= em[t];
-      if (!comp) comp = em[t];
-    }
+  int nlev = 0;
+  for (uint32_t rem = U; rem;) {
+    const uint32_t ec = eq[RB_CTZ(rem) * es];
+    rem &= ~ec;
+    const int R = RB_POPC(ec & EA) + RB_POPC(ec & EB);
+    rl += R * T.log2t[R];
+    nlev++;
   }
-  const int nlev = RB_POPC(reps);
-  // ---- MCC classification (glcm.py:679-707, see file header): components / bipartite / eigen-task
+  // ---- MCC classification (glcm.py:679-707, see file header): several components -> 1; a connected bipartite
+  // level graph (no level paired with itself, no odd cycle: 29 % of the connected graphs of i.i.d. uniform levels,
+  // all trees among them) has the eigenvalue -1 next to +1 -> 1 without a solve; else an eigen-task for phase B.
+  // One breadth-first sweep over class masks decides both (round 1 swept the pair list per question: 7 % + 18 % of
+  // this kernel's instructions, and had moved the bipartite test into the solver thread for that reason).
   double mcc;
   if (P.n_roi_levels < 2) mcc = 1.0;
   else if (nlev < 2) mcc = 0.0;
   else {
-    for (int sweep = 0; sweep < NP; sweep++) {
-      const uint32_t before = comp;
-#pragma unroll
-      for (int t = 0; t < NP; t++) if (em[t] & comp) comp |= em[t];
-      if (comp == before) break;
-    }
-    if (comp != all) mcc = 1.0;
+    bool connected, bipartite;
+    glcm_graph_scan(eq, es, EA, (int)pB[0] - (int)pA[0], U, selfpair, &connected, &bipartite);
+    if (!connected || bipartite) mcc = 1.0;
     else {
-      // connected: queued for phase B.  (A bipartite level graph -- no level paired with itself, no
-      // odd cycle -- has the eigenvalue -1 next to +1, i.e. MCC = 1 without a solve; that test is
-      // done by the solver thread on its compact edge list: here it would be paid by the whole
-      // warp whenever any lane needs it, ncu: 18 % of this kernel's instructions.)
       mcc = 0.0; acc.tasks |= 1u << s;
       acc.tcls |= (unsigned long long)glcm_task_class(nlev) << (GF_CLS_BITS * s);
     }
@@ -727,7 +557,7 @@ RB_HD void glcm_fast_voxel(const uint8_t* w, int ws, uint32_t* eq, int es, const
   double solved[GF_NA];
   GlcmSolveTables ST;
   glcm_solve_tables_from(T, ST);
-  for (int s = 0; s < GF_NA; s++) solved[s] = (tasks >> s & 1u) ? glcm_fast_solve<-1>(w, ws, ST, s, (int)(tcls >> (GF_CLS_BITS * s) & (GF_NCLS - 1))) : 0.0;
+  for (int s = 0; s < GF_NA; s++) solved[s] = (tasks >> s & 1u) ? glcm_fast_solve(w, ws, ST, s, (int)(tcls >> (GF_CLS_BITS * s) & (GF_NCLS - 1))) : 0.0;
   out[G_MCC] = glcm_fast_finish_mcc(out[G_MCC], n_ok, tasks, solved, 1);
 }
 

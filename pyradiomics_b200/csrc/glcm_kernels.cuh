@@ -16,8 +16,8 @@ namespace rb {
 //   A  one thread per centre voxel: window -> equality masks -> all 13 angles, every feature except
 //      the MCC eigen-solves; a voxel that needs k solves reserves k CONSECUTIVE 16-byte queue entries
 //      (voxel, angle slot, n_ok).  No local memory, no block barriers.
-//   B  one thread per queue entry (= one eigen-task): reloads the voxel's 27 levels and runs the
-//      sparse Lanczos + Sturm solver (glcm_fast_solve_task); result to res[k].
+//   B  one thread per queue entry (= one eigen-task): reloads the voxel's 27 levels and runs the dense register
+//      solve (<= 12 levels) or the register-resident Lanczos recurrence (13..18 levels); result to res[k].
 //   C  one thread per voxel-with-tasks adds its results in slot order to the voxel's MCC (single
 //      writer, fixed order: deterministic).  Eigen-solves are needed by a few % of the
 //      (voxel, angle) pairs on noisy data and by most on smooth data; left inline they idle most
@@ -31,12 +31,9 @@ struct GlcmTask {
   float unused;
 };
 
-// Phase B.  KIND 0: tasks with n <= 8 levels, KIND 1: 9..12 (dense register solves, see
-// glcm_small_solve), KIND 2: larger level graphs (sparse Lanczos with per-thread scratch).  Each is
-// its own kernel because the three want very different register budgets.
-#ifndef GF_LZ_SMEM
-#define GF_LZ_SMEM 0      // 1: Lanczos scratch in shared memory -- 9 % faster but produced sporadic garbage on B200 (race not found); kept off
-#endif
+// Phase B.  KIND 0: tasks with n <= 8 levels, KIND 1: 9..12 (dense register solves, see glcm_small_solve),
+// KIND 2: larger level graphs (register Lanczos, glcm_lanczos.cuh; dynamic shared memory = LZ_NARR * 18 doubles per
+// thread).  Each is its own kernel because the three want very different register budgets.
 #ifndef GF_DENSE_SYNC
 #define GF_DENSE_SYNC 1
 #endif
@@ -44,11 +41,13 @@ struct GlcmTask {
 #define GF_SOLVE_MINB_S 4
 #endif
 #ifndef GF_SOLVE_MINB_L
-#define GF_SOLVE_MINB_L 8
+#define GF_SOLVE_MINB_L 2
 #endif
 #ifndef GF_SOLVE_TILE
 #define GF_SOLVE_TILE 2048
 #endif
+constexpr int GF_LZ_SMEM_BYTES = LZ_NARR * 18 * 128 * (int)sizeof(double);
+constexpr int glcm_phaseA_smem_bytes(int nt) { return 27 * nt * (int)(sizeof(uint32_t) + sizeof(uint8_t)); }
 template <int KIND> struct SolveKind;
 template <> struct SolveKind<0> { static constexpr int lo = 0, hi = 6, minb = GF_SOLVE_MINB_S; };
 template <> struct SolveKind<1> { static constexpr int lo = 7, hi = GF_DENSE_MAX_CLS, minb = 2; };
@@ -91,6 +90,25 @@ __device__ __forceinline__ void solve_group(const uint8_t* __restrict__ lev, con
   }
 }
 
+// sorted positions [begin, end) of the tile: large tasks whose level graph has at most N nodes (N = 14 / 16 / 18)
+template <int N>
+__device__ __forceinline__ void lanczos_group(const uint8_t* __restrict__ lev, const VoxParams& P, const GlcmSolveTables& T,
+                                              const GlcmTask* __restrict__ queue, double* __restrict__ res,
+                                              const uint16_t* order, unsigned base, int begin, int end, double* scratch) {
+  for (int b0 = begin; b0 < end; b0 += 128) {
+    const int i = b0 + (int)threadIdx.x;
+    const bool live = i < end;
+    const unsigned k = base + order[live ? i : begin];
+    const GlcmTask e = queue[k];
+    uint8_t w[27];
+    glcm_task_window(lev, P, e.vi, live, w);
+    int n = 0;
+    double r = e.slot <= 2 ? glcm_lanczos_task<N>(w, 1, T, e.slot, scratch + threadIdx.x, 128, &n, live) : 1.0;
+    if (N == 18 && n == 19) r = 1.0;            // a tree (see glcm_lanczos_solve); phase A does not queue these
+    if (live) res[k] = r;
+  }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(128, SolveKind<KIND>::minb)
 glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ VoxParams P,
@@ -101,51 +119,68 @@ glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ 
   __syncthreads();
   const unsigned n = *qcount;
   // Tiles of GF_SOLVE_TILE (2048) consecutive tasks are counting-sorted by size class in shared memory, so the
-  // lanes of a warp run solves of the same size (ncu: 11-14 of 32 lanes active otherwise).
+  // lanes of a warp run solves of the same size (ncu: 11-14 of 32 lanes active otherwise).  The sort is STABLE and
+  // atomic-free (per-thread counts, one serial scan per class), so the position of a task -- and with it the batch and,
+  // for topped-up Lanczos batches, the size template that solves it -- is the same in every run: bit-reproducible maps.
   constexpr int TILE = GF_SOLVE_TILE;
+  constexpr int LO = SolveKind<KIND>::lo, KC = SolveKind<KIND>::hi - SolveKind<KIND>::lo + 1;
   __shared__ uint16_t order[TILE];
-  __shared__ int bucket[GF_NCLS];
+  __shared__ int bucket[GF_NCLS];                 // end position of each class of this kind in `order`
+  __shared__ uint16_t cnt[KC][128];               // [class][thread]: count, then exclusive prefix over the threads
   const unsigned ntiles = (n + TILE - 1) / TILE;
   for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const unsigned base = tile * TILE;
+#pragma unroll
+    for (int c = 0; c < KC; c++) cnt[c][threadIdx.x] = 0;
     if (threadIdx.x < GF_NCLS) bucket[threadIdx.x] = 0;
-    __syncthreads();
     uint8_t mycls[TILE / 128];
 #pragma unroll
     for (int j = 0; j < TILE / 128; j++) {
       const unsigned k = base + j * 128 + threadIdx.x;
       mycls[j] = k < n ? queue[k].cls : GF_NCLS;
-      if ((int)mycls[j] >= SolveKind<KIND>::lo && (int)mycls[j] <= SolveKind<KIND>::hi) atomicAdd(&bucket[mycls[j]], 1);
+      const int c = (int)mycls[j] - LO;
+      if (c >= 0 && c < KC) cnt[c][threadIdx.x]++;
     }
     __syncthreads();
-    int start = 0, ntile = 0;            // exclusive prefix of this thread's bucket (threads < GF_NCLS)
-#pragma unroll
-    for (int c = SolveKind<KIND>::lo; c <= SolveKind<KIND>::hi; c++) {
-      const int b = bucket[c];
-      if (c < (int)threadIdx.x) start += b;
-      ntile += b;
+    if ((int)threadIdx.x < KC) {                   // one thread per class: exclusive scan over the 128 per-thread counts
+      int run = 0;
+      for (int t = 0; t < 128; t++) { const int v = cnt[threadIdx.x][t]; cnt[threadIdx.x][t] = (uint16_t)run; run += v; }
+      bucket[LO + threadIdx.x] = run;              // class total (turned into the class end below)
     }
     __syncthreads();
-    if (threadIdx.x < GF_NCLS) bucket[threadIdx.x] = start;
-    __syncthreads();
+    int cstart[KC];                                // start of each class = totals of the smaller classes
+    {
+      int run = 0;
 #pragma unroll
-    for (int j = 0; j < TILE / 128; j++)
-      if ((int)mycls[j] >= SolveKind<KIND>::lo && (int)mycls[j] <= SolveKind<KIND>::hi)
-        order[atomicAdd(&bucket[mycls[j]], 1)] = (uint16_t)(j * 128 + threadIdx.x);
+      for (int c = 0; c < KC; c++) { cstart[c] = run; run += bucket[LO + c]; }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < KC) bucket[LO + threadIdx.x] += cstart[threadIdx.x];
+#pragma unroll
+    for (int j = 0; j < TILE / 128; j++) {
+      const int c = (int)mycls[j] - LO;
+      if (c >= 0 && c < KC) {
+        int cs = 0;
+#pragma unroll
+        for (int q = 0; q < KC; q++) if (q == c) cs = cstart[q];
+        order[cs + cnt[c][threadIdx.x]++] = (uint16_t)(j * 128 + threadIdx.x);
+      }
+    }
     __syncthreads();
     if (KIND == 2) {
-      RB_DYN_SHARED(float, lz_scratch);                  // [GF_LZ_SCRATCH][128]
-      for (int i = threadIdx.x; i < ntile; i += 128) {
-        const unsigned k = base + order[i];
-        const GlcmTask e = queue[k];
-        uint8_t w[27];
-        glcm_task_window(lev, P, e.vi, true, w);
-#if GF_LZ_SMEM
-        res[k] = glcm_fast_solve<2>(w, 1, T, e.slot, e.cls, lz_scratch + threadIdx.x, 128);
-#else
-        res[k] = glcm_fast_solve_task(w, 1, T, e.slot);      // per-thread local scratch
-#endif
-      }
+      RB_DYN_SHARED(double, lz_scratch);                 // [LZ_NARR * 18][128]
+      // size groups from the top; a group's last batch is topped up with tasks of the next smaller group (a larger N
+      // solves them as well: padded nodes), so a tile has ONE partially filled batch instead of three
+      const int e14 = bucket[12], e16 = bucket[14], e18 = bucket[15];
+      int s18 = e18 - (e18 - e16 + 127) / 128 * 128;
+      if (s18 < 0) s18 = 0;
+      const int e16b = s18 < e16 ? s18 : e16;
+      int s16 = e16b > e14 ? e16b - (e16b - e14 + 127) / 128 * 128 : e16b;
+      if (s16 < 0) s16 = 0;
+      const int e14b = s16 < e14 ? s16 : e14;
+      lanczos_group<18>(lev, P, T, queue, res, order, base, s18, e18, lz_scratch);
+      lanczos_group<16>(lev, P, T, queue, res, order, base, s16, e16b, lz_scratch);
+      lanczos_group<14>(lev, P, T, queue, res, order, base, 0, e14b, lz_scratch);
     } else {
       // dense solves: one template size at a time, block-uniform (idle threads run on an empty window), so the
       // barriers inside glcm_small_solve keep the warps on the same code (ncu: 8-10 no_instruction stall cycles
@@ -171,8 +206,8 @@ glcm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ ce
                  double* __restrict__ out, long long fstride, int z0, int z1, int out_z0,
                  GlcmTask* __restrict__ queue, unsigned* __restrict__ qcount) {
   __shared__ GlcmFastTables T;
-  __shared__ uint8_t wbuf[27 * NT];
-  __shared__ uint32_t eqbuf[27 * NT];
+  RB_DYN_SHARED(uint32_t, eqbuf);                                   // [27][NT] equality masks, then [27][NT] window bytes
+  uint8_t* const wbuf = reinterpret_cast<uint8_t*>(eqbuf + 27 * NT);
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(Tg);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&T);

@@ -16,7 +16,9 @@
 
 namespace rb {
 
-constexpr int GF_THREADS = 128;
+#ifndef GF_PHASEA_NT
+#define GF_PHASEA_NT 256
+#endif
 
 
 
@@ -66,73 +68,6 @@ static GlcmQueue* glcm_queue(cudaStream_t st, size_t need) {
   return &Q;
 }
 
-#if !GF_LZ_SMEM
-// EXPERIMENTAL, off unless B200_GLCM_OVERLAP=1 (prepared at the end of round 1, not yet run on hardware):
-// phase A of plane chunk i+1 on the caller's stream while the eigen-solves + finish of chunk i run on an auxiliary
-// stream, with two task queues.  Phase A is register-bound (one 256-thread CTA fills an SM's register file) and the
-// sparse solver latency-bound, so here phase A runs as ONE 128-thread CTA per SM, which leaves half of the register
-// file to solver CTAs of the previous chunk.
-struct GlcmOverlap {
-  cudaStream_t aux = nullptr;
-  GlcmQueue Q[2];
-  cudaEvent_t built[2] = {nullptr, nullptr}, solved[2] = {nullptr, nullptr};
-};
-static GlcmOverlap* glcm_overlap_state(cudaStream_t st, size_t need) {
-  static std::mutex mu;
-  static std::map<std::pair<int, cudaStream_t>, GlcmOverlap> cache;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-  std::lock_guard<std::mutex> lk(mu);
-  GlcmOverlap& O = cache[{dev, st}];
-  if (!O.aux) {
-    if (cudaStreamCreateWithFlags(&O.aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    for (int b = 0; b < 2; b++)
-      if (cudaEventCreateWithFlags(&O.built[b], cudaEventDisableTiming) != cudaSuccess ||
-          cudaEventCreateWithFlags(&O.solved[b], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-  }
-  for (int b = 0; b < 2; b++) {
-    GlcmQueue& Q = O.Q[b];
-    if (!Q.count && cudaMalloc(&Q.count, sizeof(unsigned)) != cudaSuccess) return nullptr;
-    if (Q.cap < need) {
-      if (Q.q) { cudaStreamSynchronize(st); cudaStreamSynchronize(O.aux); cudaFree(Q.q); cudaFree(Q.res); Q.q = nullptr; Q.res = nullptr; Q.cap = 0; }
-      if (cudaMalloc(&Q.q, need * sizeof(GlcmTask)) != cudaSuccess) return nullptr;
-      if (cudaMalloc(&Q.res, need * sizeof(double)) != cudaSuccess) { cudaFree(Q.q); Q.q = nullptr; return nullptr; }
-      Q.cap = need;
-    }
-  }
-  return &O;
-}
-
-static int glcm_fast_launch_overlap(const uint8_t* lev, const uint8_t* centers, const VoxParams& P, const GlcmFastTables* T,
-                                    double* out, long long fstride, int z0, int z1, int out_z0, int zchunk, int sms,
-                                    cudaStream_t st) {
-  const long long plane = (long long)P.Y * P.X;
-  GlcmOverlap* O = glcm_overlap_state(st, (size_t)zchunk * plane * GF_NA);
-  if (!O) return fail(RB_ERR_NOMEM, "could not allocate the GLCM overlap state");
-  static const int solve_bps = getenv("B200_GLCM_SOLVE_BPS") ? atoi(getenv("B200_GLCM_SOLVE_BPS")) : 8;
-  int i = 0;
-  for (int za = z0; za < z1; za += zchunk, i++) {
-    const int zb = za + zchunk < z1 ? za + zchunk : z1, b = i & 1;
-    GlcmQueue& Q = O->Q[b];
-    if (i >= 2) RB_CUDA(cudaStreamWaitEvent(st, O->solved[b], 0));          // queue b is free again
-    RB_CUDA(cudaMemsetAsync(Q.count, 0, sizeof(unsigned), st));
-    glcm_fast_kernel<2, 128><<<sms, 128, 0, st>>>(lev, centers, P, T, out, fstride, za, zb, out_z0, Q.q, Q.count);
-    RB_LAUNCH_CHECK();
-    RB_CUDA(cudaEventRecord(O->built[b], st));
-    RB_CUDA(cudaStreamWaitEvent(O->aux, O->built[b], 0));
-    glcm_fast_solve_kernel<0><<<sms * solve_bps, 128, 0, O->aux>>>(lev, P, T, Q.q, Q.count, Q.res);
-    glcm_fast_solve_kernel<1><<<sms * solve_bps, 128, 0, O->aux>>>(lev, P, T, Q.q, Q.count, Q.res);
-    glcm_fast_solve_kernel<2><<<sms * solve_bps, 128, 0, O->aux>>>(lev, P, T, Q.q, Q.count, Q.res);
-    RB_LAUNCH_CHECK();
-    glcm_fast_finish_kernel<<<sms * 8, 256, 0, O->aux>>>(P, Q.q, Q.count, Q.res, out + (long long)G_MCC * fstride, out_z0);
-    RB_LAUNCH_CHECK();
-    RB_CUDA(cudaEventRecord(O->solved[b], O->aux));
-  }
-  for (int b = 0; b < 2 && b < i; b++) RB_CUDA(cudaStreamWaitEvent(st, O->solved[b], 0));   // the caller's stream sees every MCC map
-  return RB_OK;
-}
-#endif
-
 int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P, double* out, long long fstride,
                      int z0, int z1, int out_z0, cudaStream_t st) {
   const GlcmFastTables* T = glcm_fast_tables_dev(P.Ng);
@@ -149,40 +84,39 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
   int zchunk = (int)(max_entries / (plane * GF_NA));
   if (zchunk < 1) zchunk = 1;
   if (zchunk > z1 - z0) zchunk = z1 - z0;
-#if !GF_LZ_SMEM
-  static const bool overlap = getenv("B200_GLCM_OVERLAP") && atoi(getenv("B200_GLCM_OVERLAP")) != 0;
-  if (overlap) return glcm_fast_launch_overlap((const uint8_t*)lev, centers, P, T, out, fstride, z0, z1, out_z0, zchunk, sms, st);
-#endif
   GlcmQueue* Q = glcm_queue(st, (size_t)zchunk * plane * GF_NA);
   if (!Q) return fail(RB_ERR_NOMEM, "could not allocate the GLCM eigen-task queue");
   for (int za = z0; za < z1; za += zchunk) {
     const int zb = za + zchunk < z1 ? za + zchunk : z1;
     const long long total = (long long)(zb - za) * plane;
     RB_CUDA(cudaMemsetAsync(Q->count, 0, sizeof(unsigned), st));
-    long long need = (total + GF_THREADS - 1) / GF_THREADS, cap = (long long)sms * 16;
-    const int grid = (int)(need < cap ? need : cap);
-    static const int nt = getenv("B200_GLCM_NT") ? atoi(getenv("B200_GLCM_NT")) : 256;
-    static const int minb = getenv("B200_GLCM_MINB") ? atoi(getenv("B200_GLCM_MINB")) : 1;
+    // phase A: one CTA per SM (register-bound).  384 threads at 168 registers (a few spilled words) put 12 warps on an
+    // SM instead of the 8 of the 256-thread / 236-register build; B200_GLCM_NT selects the variant for A/B runs.
+    static const int nt = getenv("B200_GLCM_NT") ? atoi(getenv("B200_GLCM_NT")) : GF_PHASEA_NT;
     const uint8_t* l8 = (const uint8_t*)lev;
-    if (nt == 256) {
-      long long need2 = (total + 255) / 256, cap2 = (long long)sms * 8;
-      const int g2 = (int)(need2 < cap2 ? need2 : cap2);
-      if (minb >= 2) glcm_fast_kernel<2, 256><<<g2, 256, 0, st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
-      else glcm_fast_kernel<1, 256><<<g2, 256, 0, st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
-    } else {
-      glcm_fast_kernel<2, 128><<<grid, 128, 0, st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
+    const long long need = (total + nt - 1) / nt, cap = (long long)sms * 8;
+    const int grid = (int)(need < cap ? need : cap);
+    static bool pa_attr[64] = {false};
+    if (!pa_attr[dev & 63]) {
+      RB_CUDA(cudaFuncSetAttribute(glcm_fast_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, glcm_phaseA_smem_bytes(256)));
+      RB_CUDA(cudaFuncSetAttribute(glcm_fast_kernel<1, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, glcm_phaseA_smem_bytes(384)));
+      RB_CUDA(cudaFuncSetAttribute(glcm_fast_kernel<1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, glcm_phaseA_smem_bytes(512)));
+      pa_attr[dev & 63] = true;
     }
+    if (nt == 512) glcm_fast_kernel<1, 512><<<grid, 512, glcm_phaseA_smem_bytes(512), st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
+    else if (nt == 384) glcm_fast_kernel<1, 384><<<grid, 384, glcm_phaseA_smem_bytes(384), st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
+    else glcm_fast_kernel<1, 256><<<grid, 256, glcm_phaseA_smem_bytes(256), st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
     RB_LAUNCH_CHECK();
     static const int solve_bps = getenv("B200_GLCM_SOLVE_BPS") ? atoi(getenv("B200_GLCM_SOLVE_BPS")) : 8;
     glcm_fast_solve_kernel<0><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
     glcm_fast_solve_kernel<1><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
-    constexpr int lz_bytes = GF_LZ_SMEM ? GF_LZ_SCRATCH * 128 * (int)sizeof(float) : 0;
+    // register Lanczos: 90 KB of per-thread shared vectors per CTA -> two CTAs per SM
     static bool lz_attr[64] = {false};
     if (!lz_attr[dev & 63]) {
-      RB_CUDA(cudaFuncSetAttribute(glcm_fast_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lz_bytes));
+      RB_CUDA(cudaFuncSetAttribute(glcm_fast_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_LZ_SMEM_BYTES));
       lz_attr[dev & 63] = true;
     }
-    glcm_fast_solve_kernel<2><<<sms * solve_bps, 128, lz_bytes, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
+    glcm_fast_solve_kernel<2><<<sms * 2, 128, GF_LZ_SMEM_BYTES, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
     RB_LAUNCH_CHECK();
     glcm_fast_finish_kernel<<<sms * 8, 256, 0, st>>>(P, Q->q, Q->count, Q->res, out + (long long)G_MCC * fstride, out_z0);
     RB_LAUNCH_CHECK();

@@ -15,6 +15,7 @@
 """
 from __future__ import annotations
 
+import collections
 import inspect
 import logging
 
@@ -42,6 +43,117 @@ def _weights(angles, spacing_zyx, norm, kind):
     return np.exp(-d ** 2) if kind == "glcm" else d
 
 
+# ---- progress reporting hook (reference radiomics/__init__.py:252-282, base.py:217,237) ------------------------
+class _DummyProgressReporter:
+    """accepts what the reference's voxel loop passes (iterable / total= / desc=) and does nothing"""
+
+    def __init__(self, iterable=None, desc="", total=None):
+        self.desc, self.iterable, self.total = desc, iterable, total
+
+    def __iter__(self):
+        return iter(self.iterable)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc_value, tb):
+        pass
+
+    def update(self, n=1):
+        pass
+
+
+progressReporter = None
+
+
+def setProgressReporter(reporter):
+    """install a tqdm-like class for the voxel-based loops (the reference's ``radiomics.progressReporter``)"""
+    global progressReporter
+    progressReporter = reporter
+
+
+def getProgressReporter(*args, **kwargs):
+    """reference radiomics/__init__.py:275-282: the configured reporter when the radiomics logger is at INFO or
+    below, else a dummy.  A reporter set on an already-imported ``radiomics`` module is honoured too."""
+    import sys
+    rep = progressReporter
+    rad = sys.modules.get("radiomics")
+    if rep is None and rad is not None:
+        rep = getattr(rad, "progressReporter", None)
+    if rep is not None and logging.getLogger("radiomics").getEffectiveLevel() <= logging.INFO:
+        return rep(*args, **kwargs)
+    return _DummyProgressReporter(*args, **kwargs)
+
+
+# ---- per-image device state shared by the feature classes (SURVEY.md section 8f rank 1) -----------------------
+def _fingerprint(a):
+    """cheap content key of a host array (shape, dtype, wrapped 64-bit sum, tail bytes): the same image handed to
+    the five classes one after the other (featureextractor.py:586-602) hits the cache; an edited image does not"""
+    a = np.ascontiguousarray(a)
+    b = a.reshape(-1).view(np.uint8)
+    n8 = b.size // 8 * 8
+    s = int(b[:n8].view(np.uint64).sum(dtype=np.uint64)) if n8 else 0
+    s2 = int(b[:n8].view(np.uint64)[::4099].sum(dtype=np.uint64)) if n8 else 0
+    return (a.shape, a.dtype.str, s, s2, bytes(b[n8:]))
+
+
+class DeviceImage:
+    """One (image, ROI mask, binning) discretised ONCE on the GPU: rb_minmax_dev -> rb_digitize_dev ->
+    rb_pack_levels_dev (reference: binImage in every class constructor, base.py:119-125, i.e. 5x per image)."""
+
+    def __init__(self, imageArray, maskArray, settings):
+        img_t = imageoperations._to_device(imageArray)
+        msk_t = imageoperations._to_device(maskArray)
+        lev_t, self.edges = imageoperations.bin_image_device(img_t, msk_t, **settings)
+        Ng = int(lev_t.max().item())
+        self.levels, presence = voxel.pack_levels(lev_t, msk_t, max(Ng, 1))
+        self.grayLevels = (torch.nonzero(presence).flatten() + 1).cpu().numpy().astype(np.int64)
+        self.Ng = int(self.grayLevels.max()) if self.grayLevels.size else 0
+        self.mask_dev = msk_t
+        self._lev32 = lev_t                     # kept until the host copy has been asked for (or never)
+        self._binned_host = None
+        self._alive = {}
+
+    def binned_host(self):
+        """the reference's ``self.imageArray`` after binning: int64 levels, 0 outside the ROI (lazy: voxel mode never needs it)"""
+        if self._binned_host is None:
+            self._binned_host = self._lev32.cpu().numpy().astype(np.int64)
+            self._lev32 = None
+        return self._binned_host
+
+    def levels3d(self):
+        return self.levels if self.levels.ndim == 3 else self.levels[None]
+
+    def glcm_alive(self, settings, centers):
+        key = (bytes(settings), None if centers is None else centers.data_ptr())
+        if key not in self._alive:
+            self._alive[key] = voxel.glcm_alive_angles(self.levels3d(), settings, centers)
+        return self._alive[key]
+
+
+_DEVICE_IMAGES = collections.OrderedDict()
+_DEVICE_IMAGES_MAX = 2
+
+
+def device_image(imageArray, maskArray, settings):
+    key = (_fingerprint(imageArray), _fingerprint(maskArray), repr(settings.get("binWidth", 25)), repr(settings.get("binCount")),
+           torch.cuda.current_device())
+    st = _DEVICE_IMAGES.get(key)
+    if st is None:
+        st = DeviceImage(imageArray, maskArray, settings)
+        _DEVICE_IMAGES[key] = st
+        while len(_DEVICE_IMAGES) > _DEVICE_IMAGES_MAX:
+            _DEVICE_IMAGES.popitem(last=False)
+    else:
+        _DEVICE_IMAGES.move_to_end(key)
+    return st
+
+
+def clear_device_cache():
+    """drop the cached device-resident discretised images"""
+    _DEVICE_IMAGES.clear()
+
+
 class RadiomicsFeaturesBase:
     """Plugin base; named like the reference's so ``radiomics.getFeatureClasses()``'s MRO-by-name
     check (reference radiomics/__init__.py:95-99) accepts subclasses."""
@@ -50,9 +162,11 @@ class RadiomicsFeaturesBase:
     MATRIX_ATTR = None    # "P_glcm", ...
 
     def __init__(self, inputImage, inputMask, **kwargs):
-        self.logger = logging.getLogger(self.__module__)
+        self.logger = logging.getLogger("radiomics." + (self.CLASS or "base"))    # reference base.py:61: the class's module
+        self.logger.debug("Initializing feature class")
         if inputImage is None or inputMask is None:
             raise ValueError("Missing input image or mask")
+        self.progressReporter = getProgressReporter
         self.settings = kwargs
         self.label = kwargs.get("label", 1)
         self.voxelBased = kwargs.get("voxelBased", False)
@@ -62,30 +176,40 @@ class RadiomicsFeaturesBase:
         self.featureNames = self.getFeatureNames()
         self.inputImage = inputImage
         self.inputMask = inputMask
-        self.imageArray = I.as_array(inputImage)
+        self._rawImageArray = I.as_array(inputImage)
+        self._imageArray = None
+        self._device = None
         labelMask = I.as_array(inputMask) == self.label
         if self.voxelBased:
             self.masked = kwargs.get("maskedKernel", True)
             self.labelledVoxelCoordinates = np.array(np.where(labelMask))
             self._centerMask = labelMask
-            self.maskArray = labelMask if self.masked else np.ones(self.imageArray.shape, dtype=bool)
+            self.maskArray = labelMask if self.masked else np.ones(self._rawImageArray.shape, dtype=bool)
         else:
             self.maskArray = labelMask
         setattr(self, self.MATRIX_ATTR, None)
-        self.imageArray = self._applyBinning(self.imageArray)
+        self._initBinning()
 
-    # ---- discretisation on the GPU (reference base.py:119-125)
-    def _applyBinning(self, matrix):
-        img_t = imageoperations._to_device(matrix)
-        msk_t = imageoperations._to_device(self.maskArray)
-        lev_t, _ = imageoperations.bin_image_device(img_t, msk_t, **self.settings)
-        Ng = int(lev_t.max().item())
-        packed, presence = voxel.pack_levels(lev_t, msk_t, max(Ng, 1))
-        self._levels_dev = packed
-        gl = (torch.nonzero(presence).flatten() + 1).cpu().numpy().astype(np.int64)
-        self.coefficients["grayLevels"] = gl
-        self.coefficients["Ng"] = int(gl.max())
-        return lev_t.cpu().numpy().astype(np.int64)
+    # ---- discretisation on the GPU, shared by the classes that see the same image (reference base.py:119-125)
+    def _initBinning(self):
+        self._device = device_image(self._rawImageArray, self.maskArray, self.settings)
+        self.coefficients["grayLevels"] = self._device.grayLevels
+        self.coefficients["Ng"] = self._device.Ng
+
+    @property
+    def imageArray(self):
+        """the discretised image like the reference's ``self.imageArray`` (host int64; downloaded on first use)"""
+        if self._imageArray is None and self._device is not None:
+            self._imageArray = self._device.binned_host()
+        return self._imageArray
+
+    @imageArray.setter
+    def imageArray(self, value):
+        self._imageArray = value
+
+    @property
+    def _levels_dev(self):
+        return self._device.levels
 
     # ---- enabling (reference base.py:127-179)
     def enableFeatureByName(self, featureName, enable=True):
@@ -124,35 +248,58 @@ class RadiomicsFeaturesBase:
 
     def _voxel_settings(self):
         kw = dict(self.settings)
-        nd = self.imageArray.ndim
+        nd = self._rawImageArray.ndim
         if nd == 2 and kw.get("force2D"):
             kw["force2Ddimension"] = kw.get("force2Ddimension", 0) + 1
         sp = self._spacing_zyx()
         kw["spacing_zyx"] = (1.0,) * (3 - nd) + tuple(sp)
         return _lib.make_settings(self.coefficients["Ng"], len(self.coefficients["grayLevels"]), **kw)
 
+    def _centers_dev(self):
+        if self.masked:
+            return None
+        c = self._centerMask if self._centerMask.ndim == 3 else self._centerMask[None]
+        return imageoperations._to_device(c)
+
+    def _map_dtype(self):
+        dt = str(self.settings.get("b200_map_dtype", "float64"))
+        if dt not in ("float64", "float32"):
+            raise ValueError("b200_map_dtype must be 'float64' (the reference's map type) or 'float32'")
+        return torch.float64 if dt == "float64" else torch.float32
+
     def _calculateVoxels(self):
-        """ONE fused kernel for the whole class (replaces the voxelBatch loop of base.py:200-245)."""
-        lev = self._levels_dev
-        if lev.ndim == 2:
-            lev = lev[None]
-        centers = None
-        if not self.masked:
-            c = self._centerMask if self._centerMask.ndim == 3 else self._centerMask[None]
-            centers = imageoperations._to_device(c)
+        """The fused kernel of the class in z-chunks; the ENABLED maps stream to page-locked host memory chunk by
+        chunk while the next chunk computes (voxel.class_maps_to_host) -- replaces the voxelBatch loop and the
+        per-voxel assignment of base.py:200-245.  `voxelBatch` is accepted and ignored."""
+        lev = self._device.levels3d()
+        names = _lib.feature_names(self.CLASS)
+        idx = [k for k, n in enumerate(names) if self.enabledFeatures.get(n)]
+        for n, enabled in self.enabledFeatures.items():
+            if enabled and n not in names:
+                self.logger.debug("Feature %s is deprecated / not computed in voxel-based mode", n)
+        if not idx:
+            return
+        settings = self._voxel_settings()
+        centers = self._centers_dev()
+        alive = self._device.glcm_alive(settings, centers) if self.CLASS == "glcm" else None
         status = torch.zeros(1, dtype=torch.int32, device=lev.device)
-        maps = voxel.voxel_features(self.CLASS, lev, self._voxel_settings(), centers=centers, status=status)
+        # b200_zrange=(z0, z1): compute and return only these planes (a multi-GPU caller hands every rank the whole image --
+        # so that bin edges, gray levels and the GLCM angle set are those of the whole ROI -- and takes one slab per rank)
+        z0, z1 = self.settings.get("b200_zrange") or (0, int(lev.shape[0]))
+        with self.progressReporter(total=int(z1 - z0), desc="planes") as pbar:
+            host = voxel.class_maps_to_host(self.CLASS, lev, settings, idx, centers=centers, alive=alive, status=status,
+                                            z0=int(z0), z1=int(z1),
+                                            zchunk=int(self.settings.get("b200_zchunk", 64)), out_dtype=self._map_dtype(),
+                                            progress=pbar.update)
         st = int(status.item())
         if st & 2:
             raise _lib.B200Error("weighted GLCM entry list overflow")
         if st & 1:
             self.logger.warning("MCC eigen-problem too large for the in-kernel solver at some voxels: NaN stored")
-        names = _lib.feature_names(self.CLASS)
-        host = maps.cpu().numpy()
-        for k, name in enumerate(names):
-            if self.enabledFeatures.get(name):
-                arr = host[k] if self.imageArray.ndim == 3 else host[k][0]
-                self.featureValues[name] = I.like(self.inputImage, np.ascontiguousarray(arr))
+        arrs = host.numpy()                      # views of ONE page-locked block the returned images keep alive
+        for pos, k in enumerate(idx):
+            arr = arrs[pos] if self._rawImageArray.ndim == 3 else arrs[pos][0]
+            self.featureValues[names[k]] = I.like(self.inputImage, arr)
 
     def _calculateSegment(self):
         self._initCalculation()
@@ -216,7 +363,20 @@ class RadiomicsGLCM(RadiomicsFeaturesBase):
         P, angles = cmatrices.calculate_glcm(self.imageArray, self.maskArray, np.array(self.settings.get("distances", [1])),
                                              self.coefficients["Ng"], f2, f2d, *self._batch_args(voxelCoordinates))
         w = _weights(angles, self._spacing_zyx(), self.weightingNorm, "glcm")
-        return np.stack([MF.glcm_process(P[v], self.coefficients["grayLevels"], self.symmetricalGLCM, w) for v in range(P.shape[0])])
+        # symmetrise / weight / drop the angles that are empty for EVERY voxel of the batch (glcm.py:149-205): one
+        # common angle axis, so the batch stacks
+        idx = np.asarray(self.coefficients["grayLevels"], int) - 1
+        P = P[:, idx][:, :, idx].astype(float)
+        if self.symmetricalGLCM:
+            P = P + P.transpose(0, 2, 1, 3)
+        if w is not None:
+            P = (P * w[None, None, None, :]).sum(3, keepdims=True)
+        tot = P.sum((1, 2))
+        if P.shape[3] > 1:
+            keep = tot.sum(0) != 0
+            P, tot = P[..., keep], tot[:, keep]
+        tot = np.where(tot == 0, np.nan, tot)
+        return P / tot[:, None, None, :]
 
     def _segment_features(self):
         return MF.glcm_features(self.P_glcm[0], self.coefficients["grayLevels"], self.coefficients["Ng"])
@@ -246,6 +406,9 @@ class RadiomicsGLRLM(RadiomicsFeaturesBase):
         P, angles = cmatrices.calculate_glrlm(self.imageArray, self.maskArray, self.coefficients["Ng"],
                                               int(np.max(self.imageArray.shape)), f2, f2d, *self._batch_args(voxelCoordinates))
         w = _weights(angles, self._spacing_zyx(), self.weightingNorm, "glrlm")
+        if P.shape[0] != 1:
+            raise NotImplementedError("P_glrlm of a voxel batch: the voxel-based path is fused (no per-voxel matrices); "
+                                      "use cmatrices.calculate_glrlm for dense per-voxel matrices")
         M, j, Nr = MF.glrlm_process(P[0], self.coefficients["grayLevels"], w)
         self.coefficients["jvector"], self.coefficients["Nr"] = j, Nr
         return M[None]
@@ -277,6 +440,8 @@ class RadiomicsGLSZM(_SizeMatrixClass):
         f2, f2d = self._matrix_args()
         P = cmatrices.calculate_glszm(self.imageArray, self.maskArray, self.coefficients["Ng"], int(np.sum(self.maskArray)),
                                       f2, f2d, *self._batch_args(voxelCoordinates))
+        if P.shape[0] != 1:
+            raise NotImplementedError("P_glszm of a voxel batch: use cmatrices.calculate_glszm for dense per-voxel matrices")
         M, j = MF.size_matrix_process(P[0], self.coefficients["grayLevels"])
         self.coefficients["jvector"] = j
         return M[None]
@@ -297,6 +462,8 @@ class RadiomicsGLDM(_SizeMatrixClass):
         f2, f2d = self._matrix_args()
         P = cmatrices.calculate_gldm(self.imageArray, self.maskArray, np.array(self.settings.get("distances", [1])),
                                      self.coefficients["Ng"], self.gldm_a, f2, f2d, *self._batch_args(voxelCoordinates))
+        if P.shape[0] != 1:
+            raise NotImplementedError("P_gldm of a voxel batch: use cmatrices.calculate_gldm for dense per-voxel matrices")
         M, j = MF.size_matrix_process(P[0], self.coefficients["grayLevels"])
         self.coefficients["jvector"] = j
         return M[None]
@@ -342,8 +509,11 @@ class RadiomicsFirstOrder(RadiomicsFeaturesBase):
         self.pixelSpacing = I.spacing_xyz(inputImage)
         self._raw = I.as_array(inputImage)
         super().__init__(inputImage, inputMask, **kwargs)
-        self.discretizedImageArray = self.imageArray
-        self.imageArray = self._raw
+        self._imageArray = self._raw          # like the reference, imageArray stays the raw intensities here
+
+    @property
+    def discretizedImageArray(self):
+        return self._device.binned_host()
 
     def _window_radii(self):
         r = int(self.settings.get("kernelRadius", 1))
@@ -371,16 +541,22 @@ class RadiomicsFirstOrder(RadiomicsFeaturesBase):
         nf = _lib.lib().rb_firstorder_num_features()
         out = torch.empty((nf, Z, Y, X), dtype=torch.float64, device=img.device)
         vv = float(np.multiply.reduce(self.pixelSpacing))
+        idx = [k for k, n in enumerate(self.NAMES) if self.enabledFeatures.get(n)]
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         _lib.check(_lib.lib().rb_firstorder_voxel_dev(
             ptr(img), imageoperations._TORCH_DT[img.dtype], ptr(msk), ptr(centers), ptr(lev), voxel.level_bytes(lev), Z, Y, X,
             rz, ry, rx, C.c_double(float(self.voxelArrayShift)), C.c_double(vv), C.c_double(float(self.settings.get("initValue", 0))),
             ptr(out), C.c_longlong(out.stride(0)), 0, Z, 0, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "firstorder")
-        host = out.cpu().numpy()
-        for k, name in enumerate(self.NAMES):
-            if self.enabledFeatures.get(name):
-                arr = host[k] if self._raw.ndim == 3 else host[k][0]
-                self.featureValues[name] = I.like(self.inputImage, np.ascontiguousarray(arr))
+        if not idx:
+            return
+        host = torch.empty((len(idx), Z, Y, X), dtype=torch.float64, pin_memory=True)     # enabled maps only
+        for pos, k in enumerate(idx):
+            host[pos].copy_(out[k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        arrs = host.numpy()
+        for pos, k in enumerate(idx):
+            arr = arrs[pos] if self._raw.ndim == 3 else arrs[pos][0]
+            self.featureValues[self.NAMES[k]] = I.like(self.inputImage, arr)
 
     def _initCalculation(self, voxelCoordinates=None):
         pass
@@ -434,8 +610,8 @@ class RadiomicsShape(RadiomicsFeaturesBase):
             raise NotImplementedError("Shape features are not available in voxel-based mode")
         super().__init__(inputImage, inputMask, **kwargs)
 
-    def _applyBinning(self, matrix):          # shape ignores intensities
-        return matrix
+    def _initBinning(self):                   # shape ignores intensities
+        self._imageArray = self._rawImageArray
 
     def _calculateVoxels(self):
         raise NotImplementedError("Shape features are not available in voxel-based mode")
@@ -444,8 +620,8 @@ class RadiomicsShape(RadiomicsFeaturesBase):
         from . import cshape
         self.pixelSpacing = np.array(self._spacing_zyx(), dtype=np.float64)
         # pad with one plane of zeros on every side (shape.py:58-72): every ROI voxel gets its 8 cubes
+        # (a local copy: self.maskArray stays the ROI mask however often this is called)
         padded = np.pad(np.asarray(self.maskArray, dtype=np.uint8), 1)
-        self.maskArray = padded != 0
         m_t = imageoperations._to_device(padded)
         self.SurfaceArea, self.Volume, self.diameters, self._n_vertices = cshape.coefficients_device(m_t, self.pixelSpacing)
         mom = cshape.moments_device(m_t)
@@ -505,7 +681,17 @@ def install(radiomics_module=None):
         classes[name] = cls
     rad.cMatrices = cmatrices
     from . import cshape
-    rad.cShape = cshape          # calculate_coefficients (3-D); the 2-D variant stays with the reference
+    # radiomics.shape2D calls cShape.calculate_coefficients2D (shape2D.py:99): the replacement forwards every name it
+    # does not implement to the reference's own _cshape, so a later import / reload of shape2D keeps working
+    orig = getattr(rad, "cShape", None)
+    if orig is not None and orig is not cshape and getattr(orig, "__name__", "") != cshape.__name__:
+        cshape._fallback = orig
+    rad.cShape = cshape
+    for mod in ("shape",):
+        try:
+            importlib.import_module(f"{rad.__name__}.{mod}").cShape = cshape
+        except ImportError:
+            pass
     for mod in ("glcm", "glrlm", "glszm", "gldm", "ngtdm", "firstorder"):
         try:
             importlib.import_module(f"{rad.__name__}.{mod}").cMatrices = cmatrices

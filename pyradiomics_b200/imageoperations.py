@@ -138,6 +138,24 @@ def binImage(parameterMatrix, parameterMatrixCoordinates=None, **kwargs):
     return out.cpu().numpy().astype(np.int64), edges
 
 
+# ------------------------------------------------------------------------------------ cropping
+def cropToTumorMask(imageNode, maskNode, boundingBox, **kwargs):
+    """reference signature (imageoperations.py:407-445): crop image and mask to the ROI's bounding box
+    `boundingBox` = (x_lo, x_hi, y_lo, y_hi, z_lo, z_hi) (inclusive, SimpleITK x,y,z order, as checkMask returns it),
+    grown by kwargs['padDistance'] voxels on every side and clipped to the image (the orchestrator passes
+    padDistance = kernelRadius in voxel-based mode, 0 otherwise: featureextractor.py:304-307,385-387).  Host-side
+    slicing (views, no copy): the crop decides which voxels ever reach the GPU."""
+    padDistance = int(kwargs.get("padDistance", 0))
+    bb = np.asarray(boundingBox, dtype=np.int64)
+    size = np.array(I.size_xyz(maskNode), dtype=np.int64)
+    nd = size.size
+    lo = np.maximum(bb[0::2][:nd] - padDistance, 0)
+    hi = np.minimum(bb[1::2][:nd] + padDistance, size - 1)
+    logger.debug("Cropping to size %s", (bb[1::2][:nd] - bb[0::2][:nd]) + 1)
+    sl = tuple(slice(int(lo[d]), int(hi[d]) + 1) for d in range(nd))[::-1]          # arrays are (z,y,x)
+    return I.like(imageNode, I.as_array(imageNode)[sl]), I.like(maskNode, I.as_array(maskNode)[sl])
+
+
 # ------------------------------------------------------------------------------------ wavelet
 # decomposition low-pass filters (PyWavelets conventions); dec_hi[k] = (-1)^(k+1) dec_lo[F-1-k]
 _DEC_LO = {

@@ -69,33 +69,9 @@ extern "C" int emul_glcm_fast(const uint16_t* lev, int Z, int Y, int X, const Vo
   return 0;
 }
 
-// debug/unit hook: MCC eigen-task of one 27-voxel window and angle slot
-extern "C" double emul_glcm_solve_window(const uint8_t* w, int slot, int Ng) {
-  GlcmFastTables* T = new GlcmFastTables;
-  glcm_fast_build_tables(*T, Ng);
-  GlcmSolveTables ST;
-  glcm_solve_tables_from(*T, ST);
-  double r = glcm_fast_solve_task(w, 1, ST, slot);
-  delete T;
-  return r;
-}
-
 #include "../../pyradiomics_b200/csrc/glrlm_fast.cuh"
-// the sparse solver with its scratch laid out like the device's shared memory ([element][thread], stride st)
-extern "C" double emul_glcm_solve_window_strided(const uint8_t* w, int slot, int Ng, int st, int lane) {
-  GlcmFastTables* T = new GlcmFastTables;
-  glcm_fast_build_tables(*T, Ng);
-  GlcmSolveTables ST;
-  glcm_solve_tables_from(*T, ST);
-  float* scr = new float[(size_t)GF_LZ_SCRATCH * st];
-  for (int i = 0; i < GF_LZ_SCRATCH * st; i++) scr[i] = 1e30f;      // poison: a wrong stride shows
-  double r = glcm_fast_solve_task(w, 1, ST, slot, scr + lane, st);
-  delete[] scr;
-  delete T;
-  return r;
-}
-
-// same task through the dispatcher (dense register solve for <= 8 levels); cls < 0: derive it
+// MCC eigen-task of one 27-voxel window and angle slot through the dispatcher (dense register solve up to 12 levels,
+// register Lanczos above); cls < 0: derive it
 extern "C" double emul_glcm_solve_window_cls(const uint8_t* w, int slot, int Ng, int cls) {
   GlcmFastTables* T = new GlcmFastTables;
   glcm_fast_build_tables(*T, Ng);
@@ -111,7 +87,7 @@ extern "C" double emul_glcm_solve_window_cls(const uint8_t* w, int slot, int Ng,
     }
     cls = glcm_task_class(n);
   }
-  double r = glcm_fast_solve<-1>(w, 1, ST, slot, cls);
+  double r = glcm_fast_solve(w, 1, ST, slot, cls);
   delete T;
   return r;
 }
@@ -185,4 +161,38 @@ extern "C" int emul_firstorder(const double* img, const uint8_t* mask, const uin
     for (int k = 0; k < FIRSTORDER_NF; k++) out[k * nvox + i] = f[k];
   }
   return 0;
+}
+
+#include "../../pyradiomics_b200/csrc/glcm_lanczos.cuh"
+// register Lanczos solver of the large axis-angle eigen-tasks: w27 = window levels with the angle axis fastest;
+// scratch laid out like the device's shared memory ([node][thread], stride st, this thread = lane)
+extern "C" double emul_glcm_lanczos_axis(const uint8_t* w27, int N, int st, int lane, int* n_out) {
+  GlcmFastTables* T = new GlcmFastTables;
+  glcm_fast_build_tables(*T, 32);
+  GlcmSolveTables ST;
+  glcm_solve_tables_from(*T, ST);
+  int wl[27];
+  for (int i = 0; i < 27; i++) wl[i] = w27[i];
+  double* sm = new double[(size_t)LZ_NARR * 18 * st];
+  for (int i = 0; i < LZ_NARR * 18 * st; i++) sm[i] = 1e300;      // poison: a wrong stride shows
+  double r = NAN;
+  if (N == 14) r = glcm_lanczos_axis<14>(wl, ST, sm + lane, st, n_out);
+  else if (N == 16) r = glcm_lanczos_axis<16>(wl, ST, sm + lane, st, n_out);
+  else if (N == 18) r = glcm_lanczos_axis<18>(wl, ST, sm + lane, st, n_out);
+  delete[] sm;
+  delete T;
+  return r;
+}
+// connectivity + bipartite sweep of phase A in position space; returns 2*connected + bipartite (eq masks from the straight-line compare block)
+extern "C" int emul_glcm_graph_scan(const uint8_t* w27, int dsh, uint32_t lo_mask, int selfpair) {
+  int wl[27]; uint32_t e[27];
+  for (int i = 0; i < 27; i++) wl[i] = w27[i];
+  RB_EQMASKS_27(wl, e);
+  uint32_t NZ = 0;
+  for (int i = 0; i < 27; i++) if (wl[i]) NZ |= 1u << i;
+  const uint32_t EA = NZ & (NZ >> dsh) & lo_mask;
+  if (!EA) return -1;
+  bool connected = false, bipartite = false;
+  glcm_graph_scan(e, 1, EA, dsh, EA | (EA << dsh), selfpair != 0, &connected, &bipartite);
+  return (connected ? 2 : 0) | (bipartite ? 1 : 0);
 }

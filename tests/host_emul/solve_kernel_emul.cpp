@@ -1,11 +1,11 @@
 // TEST-ONLY: the CUDA execution model of ONE thread block on the CPU, to run the text of
 // pyradiomics_b200/csrc/glcm_kernels.cuh (tile counting sort, size groups, block-uniform dense solves
-// with barriers, optional shared-memory Lanczos scratch) without a GPU: one std::thread per CUDA
+// with barriers, the register Lanczos with its per-thread shared-memory vectors) without a GPU: one std::thread per CUDA
 // thread, __syncthreads() = pthread barrier, __shared__ = static storage (blocks run one at a time),
 // atomics = GCC atomics.  Built with -fsanitize=thread the same run is a data-race check of the
 // kernel's shared-memory protocol.
 //
-//   g++ -O1 -g -std=c++17 -pthread [-fsanitize=thread] [-DGF_LZ_SMEM=1] -shared -fPIC solve_kernel_emul.cpp
+//   g++ -O1 -g -std=c++17 -pthread [-fsanitize=thread] -shared -fPIC solve_kernel_emul.cpp
 #include <math.h>
 #include <pthread.h>
 #include <stdint.h>
@@ -43,7 +43,7 @@ static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetc
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 #define RB_GLCM_BLOCK_SYNC 1
-static float* g_dyn_shared = nullptr;
+static double* g_dyn_shared = nullptr;
 #define RB_DYN_SHARED(type, name) type* name = (type*)g_dyn_shared
 
 #include "../../pyradiomics_b200/csrc/host_common.hpp"
@@ -57,7 +57,7 @@ static void run_kind(const uint8_t* lev, const VoxParams& P, const GlcmFastTable
   const unsigned cnt = n;
   blockDim = {128, 1, 1};
   gridDim = {(unsigned)nblocks, 1, 1};
-  std::vector<float> dyn((size_t)GF_LZ_SCRATCH * 128, 1e30f);
+  std::vector<double> dyn((size_t)LZ_NARR * 18 * 128, 1e300);
   g_dyn_shared = dyn.data();
   for (int b = 0; b < nblocks; b++) {
     blockIdx = {(unsigned)b, 0, 0};
@@ -102,7 +102,7 @@ extern "C" int emul_solve_kernels(const uint8_t* lev, int Z, int Y, int X, int N
       GlcmTask e; e.vi = vi; e.slot = (uint8_t)sl; e.n_ok = (uint8_t)n_ok; e.count = 0;
       e.cls = (uint8_t)(tcls >> (GF_CLS_BITS * sl) & (GF_NCLS - 1)); e.unused = 0.f;
       if ((int)q.size() < cap) {
-        res_direct[q.size()] = glcm_fast_solve<-1>(w, 1, ST, sl, e.cls);
+        res_direct[q.size()] = glcm_fast_solve(w, 1, ST, sl, e.cls);
         cls_out[q.size()] = e.cls;
         q.push_back(e);
       }
@@ -149,7 +149,7 @@ extern "C" long long emul_glcm_pipeline(const uint8_t* lev, int Z, int Y, int X,
   const long long plane = (long long)Y * X, fstride = (long long)Z * plane;
   std::vector<GlcmTask> q((size_t)zchunk * plane * GF_NA);
   std::vector<double> res(q.size());
-  std::vector<float> dyn((size_t)GF_LZ_SCRATCH * 128, 1e30f);
+  std::vector<double> dyn((size_t)LZ_NARR * 18 * 128, 1e300);
   g_dyn_shared = dyn.data();
   long long total_tasks = 0;
   for (int za = 0; za < Z; za += zchunk) {

@@ -238,3 +238,102 @@ def test_firstorder_voxel_maps(name, r):
         assert (arr[~m] == 0).all()
         if f not in ("Entropy", "Uniformity"):
             assert np.allclose(arr[m], z[f"{name}_{f}"][m], rtol=1e-5, atol=1e-8), f
+
+
+# ------------------------------------------------------------------------------ voxel driver / output assembly (round 2)
+def _raw_case(shape=(20, 22, 23), seed=3):
+    rng = np.random.default_rng(seed)
+    lev = rng.integers(1, 33, shape)
+    raw = ((lev - 1) * 25 + 3).astype(np.int16)
+    msk = (rng.random(shape) < 0.85).astype(np.uint8)
+    return raw, msk
+
+
+def test_plugin_voxel_path_copies_only_enabled_maps_and_matches_full_run():
+    raw, msk = _raw_case()
+    full = FC.RadiomicsGLCM(raw, msk, voxelBased=True, binWidth=25).execute()
+    obj = FC.RadiomicsGLCM(raw, msk, voxelBased=True, binWidth=25)
+    obj.enableFeatureByName("MCC")
+    obj.enableFeatureByName("Contrast")
+    obj.enableFeatureByName("SumSquares")
+    part = obj.execute()
+    assert sorted(part) == ["Contrast", "MCC", "SumSquares"]
+    for k, v in part.items():
+        assert np.array_equal(v.array, full[k].array, equal_nan=True)
+    # the three maps are views of ONE page-locked block of exactly three maps
+    base = part["MCC"].array.base
+    assert base is not None and base.shape[0] == 3
+
+
+def test_plugin_shares_one_discretisation_between_the_classes():
+    raw, msk = _raw_case(seed=4)
+    FC.clear_device_cache()
+    objs = [FC.FEATURE_CLASSES[c](raw, msk, voxelBased=True, binWidth=25) for c in FC.FEATURE_CLASSES]
+    assert len({id(o._device) for o in objs}) == 1                  # binned once, shared (base.py:119-125 runs it 5x)
+    raw2 = raw.copy()
+    raw2[3, 4, 5] += 400                                            # an edited image must not hit the cache
+    assert FC.RadiomicsGLCM(raw2, msk, voxelBased=True, binWidth=25)._device is not objs[0]._device
+    # the lazily downloaded discretised array equals the reference's binImage
+    ref, _, levels, Ng = PL.bin_image(raw, msk.astype(bool), 25)
+    assert np.array_equal(objs[0].imageArray, ref) and objs[0].coefficients["Ng"] == Ng
+    assert np.array_equal(objs[0].coefficients["grayLevels"], levels)
+
+
+@pytest.mark.parametrize("cname", ["glcm", "ngtdm"])
+def test_plugin_zrange_and_float32_maps(cname):
+    raw, msk = _raw_case(seed=5)
+    cls = FC.FEATURE_CLASSES[cname]
+    full = cls(raw, msk, voxelBased=True, binWidth=25, b200_zchunk=7).execute()
+    slab = cls(raw, msk, voxelBased=True, binWidth=25, b200_zrange=(6, 15), b200_zchunk=4).execute()
+    f32 = cls(raw, msk, voxelBased=True, binWidth=25, b200_map_dtype="float32", b200_zchunk=5).execute()
+    for k in full:
+        a = full[k].array
+        assert slab[k].array.shape == (9,) + raw.shape[1:]
+        assert np.array_equal(slab[k].array, a[6:15], equal_nan=True)       # same bits as the whole-volume run
+        assert f32[k].array.dtype == np.float32
+        assert np.array_equal(f32[k].array, a.astype(np.float32), equal_nan=True)
+
+
+def test_plugin_progress_reporter_and_logger_names():
+    import logging
+    raw, msk = _raw_case(seed=6)
+    seen = []
+
+    class Rep:
+        def __init__(self, iterable=None, desc="", total=None):
+            seen.append(("init", total))
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            seen.append(("exit",))
+
+        def update(self, n=1):
+            seen.append(("update", n))
+
+    FC.setProgressReporter(Rep)
+    lg = logging.getLogger("radiomics")
+    old = lg.level
+    lg.setLevel(logging.INFO)
+    try:
+        obj = FC.RadiomicsGLDM(raw, msk, voxelBased=True, binWidth=25, b200_zchunk=8)
+        assert obj.logger.name == "radiomics.gldm"                   # reference base.py:61: the class's module logger
+        obj.execute()
+    finally:
+        FC.setProgressReporter(None)
+        lg.setLevel(old)
+    assert seen[0] == ("init", raw.shape[0]) and seen[-1] == ("exit",)
+    assert sum(s[1] for s in seen if s[0] == "update") == raw.shape[0]
+
+
+def test_host_extractor_float32_and_float64_agree():
+    from pyradiomics_b200 import voxel
+    rng = np.random.default_rng(8)
+    lev = rng.integers(1, 33, (18, 19, 20)).astype(np.int32)
+    msk = np.ones(lev.shape, np.uint8)
+    a = voxel.HostExtractor(lev.shape, zchunk=5).run(lev, msk, 32, 32)
+    a = {c: t.clone() for c, t in a.items()}
+    b = voxel.HostExtractor(lev.shape, zchunk=7, out_dtype=torch.float32).run(lev, msk, 32, 32)
+    for c in a:
+        assert torch.equal(a[c].to(torch.float32), b[c]) or torch.allclose(a[c].to(torch.float32), b[c], equal_nan=True, rtol=0, atol=0)

@@ -1,7 +1,7 @@
 """The eigen-task kernels' ORCHESTRATION on the CPU box: tests/host_emul/solve_kernel_emul.cpp runs the text of
 csrc/glcm_kernels.cuh with one std::thread per CUDA thread (barriers as barriers, shared memory as static
-storage): the tile counting sort, the size groups, the block-uniform dense solves with their barriers and both scratch
-variants of the sparse solver must hand every queued task to exactly one solver and reproduce the direct solve."""
+storage): the tile counting sort, the size groups, the block-uniform dense solves with their barriers and the register
+Lanczos groups (per-thread shared vectors) must hand every queued task to exactly one solver and reproduce the direct solve."""
 import ctypes as C
 import os
 import subprocess
@@ -27,25 +27,27 @@ def _build(tag, defs):
     return _LIBS[tag]
 
 
-@pytest.mark.parametrize("tag,defs", [("local", []), ("smem", ["-DGF_LZ_SMEM=1"])])
-@pytest.mark.parametrize("kind,n", [("smooth", 12), ("uniform", 14)])
-def test_emulated_solve_kernels_process_every_task_once(tag, defs, kind, n):
-    lib = _build(tag, defs)
+@pytest.mark.parametrize("kind,n", [("smooth", 12), ("uniform", 16)])
+def test_emulated_solve_kernels_process_every_task_once(kind, n):
+    lib = _build("local", [])
     lev = np.ascontiguousarray(bench.synth_volume(40, kind)[:n, :n, :n].astype(np.uint8))
     cap = 100000
     rk, rd, cls = np.zeros(cap), np.zeros(cap), np.zeros(cap, np.int32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     nt = lib.emul_solve_kernels(p(lev), n, n, n, 32, 3, cap, p(rk), p(rd), p(cls))
-    assert 1000 < nt < cap
+    assert 800 < nt < cap
     rk, rd, cls = rk[:nt], rd[:nt], cls[:nt]
     assert not (rk == -12345.0).any(), "a queued task was not picked up by any solve kernel"
     assert not np.isnan(rk).any()
-    assert np.array_equal(rk, rd)                       # same code, same inputs: bit-identical to the direct solve
+    dense = cls <= 10
+    assert np.array_equal(rk[dense], rd[dense])         # same code, same inputs: bit-identical to the direct solve
+    # large tasks may be topped up into a batch of the next larger Lanczos size (padded nodes): same value to rounding
+    assert np.allclose(rk[~dense], rd[~dense], rtol=0, atol=1e-12)
     hist = np.bincount(cls, minlength=16)
     assert hist[:7].sum() and hist[7:11].sum() and hist[11:].sum()      # all three kernels had work
 
 
-@pytest.mark.parametrize("kind,n", [("smooth", 12), ("uniform", 13)])
+@pytest.mark.parametrize("kind,n", [("smooth", 12), ("uniform", 14)])
 def test_emulated_glcm_pipeline_equals_per_voxel_math(kind, n):
     """phase A kernel (per-angle barriers, atomic queue reservation, non-centre voxels) -> three solve kernels -> finish
     kernel, in plane chunks like glcm_fast_launch, against the single-thread composition of the same math
@@ -64,10 +66,13 @@ def test_emulated_glcm_pipeline_equals_per_voxel_math(kind, n):
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     out = np.zeros((24, n, n, n))
     ntasks = pipe.emul_glcm_pipeline(p(lev), n, n, n, 32, 5, p(out))           # 3 plane chunks
-    assert ntasks > 1000
+    assert ntasks > 700
     ref = np.zeros((24, n, n, n))
     s = _lib.make_settings(32, 32)
     lev16 = lev.astype(np.uint16)
     assert emul.emul_glcm_fast(p(lev16), n, n, n, C.byref(s), None, p(ref)) == 0
     for k, name in enumerate(_lib.feature_names("glcm")):
-        assert np.array_equal(out[k], ref[k], equal_nan=True), name
+        if name == "MCC":              # Lanczos tasks may run in a larger size class than the single-thread composition picks
+            assert np.allclose(out[k], ref[k], rtol=0, atol=1e-12, equal_nan=True), name
+        else:
+            assert np.array_equal(out[k], ref[k], equal_nan=True), name
