@@ -158,6 +158,24 @@ int rb_calculate_glszm(const int32_t *image, const uint8_t *mask, const int *siz
 int rb_fill_glszm(void *handle, int Ng, int max_region, double *glszm);
 void rb_glszm_release(void *handle);
 
+/* Segment-based matrices straight from a DEVICE-resident packed level volume (rb_pack_levels_dev) -- what the plugin
+ * classes call once the image has been discretised on the GPU, instead of shipping it back to the host for the entry
+ * points above.  Same matrices / layouts / angle order; results in HOST float64 buffers; synchronous.
+ * rb_segment_texture_dev builds GLCM, GLDM and NGTDM in ONE pass over the volume (NULL = not wanted): a CTA stages a box
+ *   of the level volume in shared memory -- through TMA (cp.async.bulk.tensor.3d with hardware zero-fill outside the
+ *   volume) when the row pitch is a multiple of 16 bytes, else by cooperative loads -- and accumulates the three
+ *   matrices in shared-memory histograms (reference radiomics/src/cmatrices.c:4-92, 660-754, 543-658).  `distances`
+ *   drives all three (the GLCM uses the unidirectional half of the offsets).
+ * rb_segment_glrlm_dev: every run END walks back to the start of its run (cmatrices.c:299-541).
+ * rb_segment_glszm_dev: phase one of GLSZM as rb_calculate_glszm (finish with rb_fill_glszm / rb_glszm_release). */
+int rb_segment_texture_dev(const void *levels_dev, int level_bytes, const int *size, int nd, const int *distances,
+                           int ndist, int Ng, int alpha, int force2D, int force2Ddimension, double *glcm, double *gldm,
+                           double *ngtdm, int *angles);
+int rb_segment_glrlm_dev(const void *levels_dev, int level_bytes, const int *size, int nd, int Ng, int Nr, int force2D,
+                         int force2Ddimension, double *glrlm, int *angles);
+int rb_segment_glszm_dev(const void *levels_dev, int level_bytes, const int *size, int nd, int Ng, int force2D,
+                         int force2Ddimension, int *max_region, void **handle);
+
 /* ---- gray-level discretisation and pre-filters (device pointers, asynchronous) --------------
  * dtype codes for `image_dev`: 0 int16, 1 int32, 2 float32, 3 float64, 4 uint8, 5 uint16, 6 int64.
  * rb_minmax_dev: ROI minimum / maximum (mask_dev may be NULL = all voxels) as order-preserving
@@ -177,6 +195,16 @@ int rb_digitize_dev(const void *image_dev, int dtype, const uint8_t *mask_dev, l
  * `flen` decomposition taps.  Odd lengths behave like the reference's wrap-pad-then-crop. */
 int rb_swt_axis_dev(const double *in_dev, int Z, int Y, int X, int axis, const double *dec_lo,
                     const double *dec_hi, int flen, double *out_lo_dev, double *out_hi_dev, void *stream);
+/* All three axes at once for a 3-D volume: the 8 sub-bands of one level in a single pass (input staged through shared
+ * memory plane by plane, a ring of xy-filtered planes feeds the z filter).  Periodic extension in all axes -- wrap-pad odd
+ * sizes first, as the reference does (radiomics/imageoperations.py:914-919).  Sub-band b = bx + 2*by + 4*bz (bit set =
+ * high-pass 'd' along that axis; pywt's key is the letters in x,y,z order because the reference passes axes=(2,1,0),
+ * imageoperations.py:871,935) is written to out_dev[b * band_stride + voxel].  flen in {2, 4, 6, 8}.
+ * Only planes [z_begin, z_end) are produced (out plane 0 = input plane z_begin): a multi-GPU caller passes its z-slab
+ * with (flen-1-flen/2) halo planes below and flen/2 above, exchanged ring-closed between the ranks, and asks for the
+ * interior -- the z wrap-around is then never taken; 0, Z = the whole (periodic) volume. */
+int rb_swt3d_dev(const double *in_dev, int Z, int Y, int X, const double *dec_lo, const double *dec_hi, int flen,
+                 double *out_dev, long long band_stride, int z_begin, int z_end, void *stream);
 /* One axis of a 4th-order recursive (IIR) Gaussian / Gaussian-derivative filter, causal +
  * anti-causal, the building block of ITK's LaplacianRecursiveGaussianImageFilter used at
  * radiomics/imageoperations.py:824-830.  coef20 (HOST) = N0..N3, D1..D4, M1..M4, BN1..4, BM1..4;

@@ -75,3 +75,35 @@ def recursive_gaussian_axis(x, coef, axis):
         a4, a3, a2, a1 = a3, a2, a1, x[i]
         b4, b3, b2, b1 = b3, b2, b1, y
     return np.moveaxis(out, 0, axis)
+
+
+def swt3_levels(x, lo, hi, axes, level=1, start_level=0):
+    """restatement of the reference's _swt3 (radiomics/imageoperations.py:899-970) around swtn_level1: the odd axes are
+    wrap-padded by one sample ONCE (:914-919), every level is a level-1 transform of the previous (still padded)
+    approximation (:924-937), start_level discards the first levels, and only what is handed out is cropped (:947-963).
+    Returns (approximation, [ {band: array} per kept level ])."""
+    x = np.asarray(x, float)
+    orig = x.shape
+    pad = [(0, 1 if (d in axes and x.shape[d] % 2) else 0) for d in range(x.ndim)]
+    data = np.pad(x, pad, "wrap")
+    crop = tuple(slice(0, n) for n in orig)
+    key_a = "a" * len(axes)
+
+    def one(d):
+        cur = {"": d}
+        for ax in axes:                       # plain periodic convolution on the even-sized padded array
+            nxt = {}
+            for k, v in cur.items():
+                nxt[k + "a"] = swt_axis(v, lo, ax)
+                nxt[k + "d"] = swt_axis(v, hi, ax)
+            cur = nxt
+        return cur
+
+    for _ in range(start_level):
+        data = one(data)[key_a]
+    out = []
+    for _ in range(start_level, start_level + level):
+        dec = one(data)
+        data = dec[key_a]
+        out.append({k: v[crop] for k, v in dec.items() if k != key_a})
+    return data[crop], out

@@ -51,7 +51,7 @@ def _compile_and_link(out: str, extra: list[str], objdir: str, verbose: bool = F
         for rc in ex.map(lambda j: subprocess.call(j[2], cwd=CSRC), jobs):
             if rc:
                 raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out, *[j[1] for j in jobs], "-lcuda"], cwd=CSRC)
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out, *[j[1] for j in jobs]], cwd=CSRC)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

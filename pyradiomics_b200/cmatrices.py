@@ -120,3 +120,59 @@ def calculate_gldm(image, mask, distances, Ng, alpha, force2D, force2Ddimension,
                                   int(bool(force2D)), int(force2Ddimension), int(kernelRadius), _p(v), nvox, _p(out)),
           "GLDM")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Device-resident variants: the same matrices from a packed level volume that is already on the GPU (a CUDA tensor from
+# rb_pack_levels_dev) -- what the plugin classes use in segment-based mode, so the discretised image never returns to
+# the host (the reference hands cMatrices the host array it binned in Python, radiomics/glcm.py:145 etc.).
+def _dev_args(levels):
+    import torch
+    assert isinstance(levels, torch.Tensor) and levels.is_cuda and levels.is_contiguous() and levels.ndim in (2, 3)
+    size = np.array(levels.shape, dtype=np.int32)
+    lb = 1 if levels.dtype == torch.uint8 else 2
+    return C.c_void_p(levels.data_ptr()), lb, size
+
+
+def segment_texture_device(levels, distances, Ng, alpha, force2D, force2Ddimension, glcm=True, gldm=True, ngtdm=True):
+    """GLCM, GLDM and NGTDM of one ROI in ONE pass over the device-resident level volume (rb_segment_texture_dev):
+    {"glcm": (P [1,Ng,Ng,Na], angles), "gldm": P [1,Ng,2*Na_bi+1], "ngtdm": P [1,Ng,3]} for the requested ones"""
+    ptr, lb, size = _dev_args(levels)
+    d = _distances(distances)
+    ang = generate_angles(size, d, 0, force2D, force2Ddimension)
+    ang_bi = generate_angles(size, d, 1, force2D, force2Ddimension)
+    out = {}
+    P_glcm = np.empty((1, Ng, Ng, ang.shape[0]), dtype=np.float64) if glcm else None
+    P_gldm = np.empty((1, Ng, 2 * ang_bi.shape[0] + 1), dtype=np.float64) if gldm else None
+    P_ngtdm = np.empty((1, Ng, 3), dtype=np.float64) if ngtdm else None
+    check(lib().rb_segment_texture_dev(ptr, lb, _p(size), int(size.size), _p(d), int(d.size), int(Ng), int(alpha), int(bool(force2D)),
+                                       int(force2Ddimension), _p(P_glcm), _p(P_gldm), _p(P_ngtdm), None), "GLCM/GLDM/NGTDM")
+    if glcm:
+        out["glcm"] = (P_glcm, ang)
+    if gldm:
+        out["gldm"] = P_gldm
+    if ngtdm:
+        out["ngtdm"] = P_ngtdm
+    return out
+
+
+def calculate_glrlm_device(levels, Ng, Nr, force2D, force2Ddimension):
+    ptr, lb, size = _dev_args(levels)
+    ang = generate_angles(size, [1], 0, force2D, force2Ddimension)
+    out = np.empty((1, Ng, int(Nr), ang.shape[0]), dtype=np.float64)
+    check(lib().rb_segment_glrlm_dev(ptr, lb, _p(size), int(size.size), int(Ng), int(Nr), int(bool(force2D)), int(force2Ddimension),
+                                     _p(out), None), "GLRLM")
+    return out, ang
+
+
+def calculate_glszm_device(levels, Ng, force2D, force2Ddimension):
+    ptr, lb, size = _dev_args(levels)
+    generate_angles(size, [1], 1, force2D, force2Ddimension)
+    mx = C.c_int(0)
+    handle = C.c_void_p()
+    check(lib().rb_segment_glszm_dev(ptr, lb, _p(size), int(size.size), int(Ng), int(bool(force2D)), int(force2Ddimension),
+                                     C.byref(mx), C.byref(handle)), "GLSZM")
+    max_region = max(1, mx.value)
+    out = np.empty((1, Ng, max_region), dtype=np.float64)
+    check(lib().rb_fill_glszm(handle, int(Ng), max_region, _p(out)), "GLSZM")
+    return out

@@ -50,10 +50,14 @@ static bool force_generic() {
 
 int calculate_matrix_host(int mode, const int32_t* image, const uint8_t* mask, const int* size, int nd,
                           const int* distances, int ndist, int Ng, int Nr, int alpha, int force2D, int force2Ddimension,
-                          int kernelRadius, const int* voxels, int nvox, double* out_host, int* angles_out, int* na_out);
+                          int kernelRadius, const int* voxels, int nvox, double* out_host, int* angles_out, int* na_out,
+                          const void* levels_dev = nullptr);
 int glszm_zones_host(const int32_t* image, const uint8_t* mask, const int* size, int nd, int Ng, int force2D,
                      int force2Ddimension, int kernelRadius, const int* voxels, int nvox, int* max_region_out,
-                     void** handle_out);
+                     void** handle_out, const void* levels_dev = nullptr);
+int segment_tile_matrices(const uint8_t* lev, int nd, int Z, int Y, int X, const int* distances, int ndist, int Ng, int alpha,
+                          int force2D, int force2Ddimension, double* glcm_host, double* gldm_host, double* ngtdm_host,
+                          int* angles_out, int* na_out, cudaStream_t st);
 int glszm_fill_host(void* handle, int Ng, int max_region, double* out_host);
 void glszm_release(void* handle);
 
@@ -67,6 +71,8 @@ int swt_axis_launch(const double* in, int Z, int Y, int X, int axis, const doubl
                     double* out_lo, double* out_hi, cudaStream_t st);
 int recursive_gauss_launch(const void* in, int in_is_f32, int Z, int Y, int X, int axis, const double* coef20, float* out,
                            double* scratch, double scale, int accumulate, cudaStream_t st);
+int swt3d_launch(const double* in, int Z, int Y, int X, const double* lo, const double* hi, int F, double* out,
+                 long long band_stride, int z_begin, int z_end, cudaStream_t st);
 
 int firstorder_launch(const void* img, int dtype, const uint8_t* mask, const uint8_t* centers, const void* lev,
                       int level_bytes, int Z, int Y, int X, int rz, int ry, int rx, double shift, double voxel_volume,
@@ -266,6 +272,39 @@ int rb_calculate_ngtdm(const int32_t* image, const uint8_t* mask, const int* siz
   return calculate_matrix_host(2, image, mask, size, nd, distances, ndist, Ng, 0, 0, force2D, force2Ddimension,
                                kernelRadius, voxels, nvox, ngtdm, NULL, NULL);
 }
+// ---- segment-mode matrices from a device-resident packed level volume (no host round trip of the image)
+int rb_segment_texture_dev(const void* levels_dev, int level_bytes, const int* size, int nd, const int* distances, int ndist,
+                           int Ng, int alpha, int force2D, int force2Ddimension, double* glcm, double* gldm, double* ngtdm,
+                           int* angles) {
+  if (!levels_dev || !size || (nd != 2 && nd != 3)) return fail(RB_ERR_ARG, "levels / size");
+  if (level_bytes != rb_level_bytes(Ng)) return fail(RB_ERR_ARG, "level_bytes does not match Ng");
+  int dmax = 0;
+  for (int i = 0; i < ndist; i++) dmax = distances[i] > dmax ? distances[i] : dmax;
+  const int Z = nd == 3 ? size[0] : 1, Y = size[nd - 2], X = size[nd - 1];
+  if (level_bytes == 1 && dmax <= 3) {
+    const int rc = segment_tile_matrices((const uint8_t*)levels_dev, nd, Z, Y, X, distances, ndist, Ng, alpha, force2D,
+                                         force2Ddimension, glcm, gldm, ngtdm, angles, NULL, 0);
+    if (rc != RB_ERR_UNSUPPORTED) return rc;
+  }
+  int rc = RB_OK;        // 16-bit levels / long offsets / very many levels: one class at a time through round 1's kernels
+  if (glcm) rc = calculate_matrix_host(0, NULL, NULL, size, nd, distances, ndist, Ng, 0, 0, force2D, force2Ddimension, 0, NULL, 1, glcm, angles, NULL, levels_dev);
+  if (!rc && gldm) rc = calculate_matrix_host(1, NULL, NULL, size, nd, distances, ndist, Ng, 0, alpha, force2D, force2Ddimension, 0, NULL, 1, gldm, NULL, NULL, levels_dev);
+  if (!rc && ngtdm) rc = calculate_matrix_host(2, NULL, NULL, size, nd, distances, ndist, Ng, 0, 0, force2D, force2Ddimension, 0, NULL, 1, ngtdm, NULL, NULL, levels_dev);
+  return rc;
+}
+int rb_segment_glrlm_dev(const void* levels_dev, int level_bytes, const int* size, int nd, int Ng, int Nr, int force2D,
+                         int force2Ddimension, double* glrlm, int* angles) {
+  if (!levels_dev || !size || (nd != 2 && nd != 3)) return fail(RB_ERR_ARG, "levels / size");
+  if (level_bytes != rb_level_bytes(Ng)) return fail(RB_ERR_ARG, "level_bytes does not match Ng");
+  return calculate_matrix_host(3, NULL, NULL, size, nd, NULL, 0, Ng, Nr, 0, force2D, force2Ddimension, 0, NULL, 1, glrlm, angles, NULL, levels_dev);
+}
+int rb_segment_glszm_dev(const void* levels_dev, int level_bytes, const int* size, int nd, int Ng, int force2D,
+                         int force2Ddimension, int* max_region, void** handle) {
+  if (!levels_dev || !size || (nd != 2 && nd != 3)) return fail(RB_ERR_ARG, "levels / size");
+  if (level_bytes != rb_level_bytes(Ng)) return fail(RB_ERR_ARG, "level_bytes does not match Ng");
+  return glszm_zones_host(NULL, NULL, size, nd, Ng, force2D, force2Ddimension, 0, NULL, 1, max_region, handle, levels_dev);
+}
+
 int rb_calculate_glszm(const int32_t* image, const uint8_t* mask, const int* size, int nd, int Ng, int force2D,
                        int force2Ddimension, int kernelRadius, const int* voxels, int nvox, int* max_region,
                        void** handle) {
@@ -292,6 +331,11 @@ int rb_swt_axis_dev(const double* in_dev, int Z, int Y, int X, int axis, const d
   if (axis < 0 || axis > 2) return fail(RB_ERR_ARG, "axis must be 0..2");
   return swt_axis_launch(in_dev, Z, Y, X, axis, dec_lo, dec_hi, flen, out_lo_dev, out_hi_dev, (cudaStream_t)stream);
 }
+int rb_swt3d_dev(const double* in_dev, int Z, int Y, int X, const double* dec_lo, const double* dec_hi, int flen,
+                 double* out_dev, long long band_stride, int z_begin, int z_end, void* stream) {
+  return swt3d_launch(in_dev, Z, Y, X, dec_lo, dec_hi, flen, out_dev, band_stride, z_begin, z_end, (cudaStream_t)stream);
+}
+
 int rb_recursive_gaussian_axis_dev(const void* in_dev, int in_is_f32, int Z, int Y, int X, int axis, const double* coef20,
                                    float* out_dev, double* scratch_dev, double scale, int accumulate, void* stream) {
   if (axis < 0 || axis > 2) return fail(RB_ERR_ARG, "axis must be 0..2");

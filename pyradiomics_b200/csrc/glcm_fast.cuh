@@ -402,32 +402,50 @@ RB_HD void glcm_fast_angle(const uint8_t* w, int ws, const uint32_t* eq, int es,
     if (P.alive[orig >> 5] >> (orig & 31) & 1u) acc.ja_nan = true;
     return;
   }
-  // ---- level classes of the pair ends (one visit per class, not per pair end): marginal entropy.
+  // ---- level classes of the pair ends: marginal entropy and the level graph of this angle.
   // R(level) = number of matrix entries in its row = popcount(class & EA) + popcount(class & EB);
-  // sum_levels R log2 R feeds HX = HY.
-  const uint32_t U = EA | EB;
+  // sum_levels R log2 R = sum over the 2n pair ends of log2 R(their level).
+  // (Straight-line per-pair code on purpose: a loop over the classes with its shared-memory load in the carried
+  // dependence measured 25 % slower for the whole kernel -- 8 to 16 warps per SM cannot hide a 30-cycle chain per class.)
   double rl = 0;
-  int nlev = 0;
-  for (uint32_t rem = U; rem;) {
-    const uint32_t ec = eq[RB_CTZ(rem) * es];
-    rem &= ~ec;
-    const int R = RB_POPC(ec & EA) + RB_POPC(ec & EB);
-    rl += R * T.log2t[R];
-    nlev++;
+  uint32_t reps = 0, all = 0, comp = 0;
+  uint32_t em[NP];
+#pragma unroll
+  for (int t = 0; t < NP; t++) {
+    em[t] = 0;
+    if (valid >> t & 1u) {
+      const uint32_t ea = eq[pA[t] * es], eb = eq[pB[t] * es];
+      rl += T.log2t[RB_POPC(ea & EA) + RB_POPC(ea & EB)] + T.log2t[RB_POPC(eb & EA) + RB_POPC(eb & EB)];
+      reps |= (ea & (0u - ea)) | (eb & (0u - eb));          // lowest position of each class
+      em[t] = ea | eb;
+      all |= em[t];
+      if (!comp) comp = em[t];
+    }
   }
+  const int nlev = RB_POPC(reps);
   // ---- MCC classification (glcm.py:679-707, see file header): several components -> 1; a connected bipartite
   // level graph (no level paired with itself, no odd cycle: 29 % of the connected graphs of i.i.d. uniform levels,
   // all trees among them) has the eigenvalue -1 next to +1 -> 1 without a solve; else an eigen-task for phase B.
-  // One breadth-first sweep over class masks decides both (round 1 swept the pair list per question: 7 % + 18 % of
-  // this kernel's instructions, and had moved the bipartite test into the solver thread for that reason).
   double mcc;
   if (P.n_roi_levels < 2) mcc = 1.0;
   else if (nlev < 2) mcc = 0.0;
   else {
-    bool connected, bipartite;
-    glcm_graph_scan(eq, es, EA, (int)pB[0] - (int)pA[0], U, selfpair, &connected, &bipartite);
-    if (!connected || bipartite) mcc = 1.0;
+    for (int sweep = 0; sweep < NP; sweep++) {
+      const uint32_t before = comp;
+#pragma unroll
+      for (int t = 0; t < NP; t++) if (em[t] & comp) comp |= em[t];
+      if (comp == before) break;
+    }
+    bool bipartite = false;
+    if (comp == all && !selfpair) {
+      // 2-colouring by a breadth-first sweep over class masks (<= 2 nlev closure steps; round 1 swept the pair list
+      // instead -- 18 % of this kernel's instructions -- and had moved the test into the solver thread for that reason)
+      bool connected;
+      glcm_graph_scan(eq, es, EA, (int)pB[0] - (int)pA[0], EA | EB, false, &connected, &bipartite, true);
+    }
+    if (comp != all || bipartite) mcc = 1.0;
     else {
+      // connected, not bipartite: queued for phase B
       mcc = 0.0; acc.tasks |= 1u << s;
       acc.tcls |= (unsigned long long)glcm_task_class(nlev) << (GF_CLS_BITS * s);
     }

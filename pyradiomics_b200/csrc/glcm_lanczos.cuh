@@ -17,8 +17,10 @@
 //     shared-memory vectors U (= y1) and S (neighbour sums), laid out [node][thread] so a warp's 64-bit
 //     accesses are always two conflict-free wavefronts whatever the node indices are;
 //   * every loop has a compile-time trip count (N = 14 / 16 / 18 by size class): a warp's lanes never
-//     diverge; a breakdown (invariant subspace) just continues with zero vectors, which appends decoupled
-//     zero eigenvalues to the tridiagonal -- harmless for max(|hi|, |lo|).
+//     diverge; a breakdown (invariant subspace) just continues with zero vectors, which leaves decoupled
+//     zero eigenvalues in the tridiagonal -- harmless for max(|hi|, |lo|).  Padded nodes (n < N) contribute exact zeros
+//     to every sum and the eigenvalue search looks at the leading (n-1) x (n-1) block only, so a task's result is
+//     bit-identical whichever size template solves it.
 // __host__ __device__: tests/host_emul checks the arithmetic against LAPACK on the CPU box (test-only).
 #pragma once
 // (included from the middle of glcm_fast.cuh: needs GlcmSolveTables, glcm_eq_positions, tridiag_extreme_pair_static)
@@ -30,6 +32,81 @@ constexpr int LZ_ACC = 3;                     // interleaved partial sums per re
 constexpr int LZ_NARR = 5;                    // per-thread shared arrays: U, S, IR, D, E (N doubles each)
 
 RB_HD constexpr int lz_smem_doubles(int N) { return LZ_NARR * N; }
+
+// Both extreme eigenvalues of the leading m x m block of a symmetric tridiagonal held in registers (d[0..NMAX-1],
+// e[1..NMAX-1]); the loops have the compile-time bound NMAX and rows >= m are predicated off, so that the SAME task gives
+// bit-identical results whichever size template (NMAX >= m) happens to solve it -- the maps do not depend on how the
+// eigen-task queue was filled.  Laguerre from outside the spectrum for both ends in one loop, Sturm bisection for an end
+// that has not settled (as tridiag_extreme_pair_static).
+template <int NMAX>
+RB_HD double tridiag_bisect_dyn(const double* d, const double* e, int m, double lo, double hi, int k) {
+  for (int it = 0; it < 36; it++) {
+    const double xm = 0.5 * (lo + hi);
+    double pm2 = 1.0, pm1 = d[0] - xm;
+    int cnt = pm1 <= 0;
+#pragma unroll
+    for (int i = 1; i < NMAX; i++) {
+      if (i < m) {
+        const double e2 = e[i] * e[i];
+        if (e2 == 0) { pm2 = 1.0; pm1 = d[i] - xm; cnt += pm1 <= 0; }
+        else {
+          const double p = (d[i] - xm) * pm1 - e2 * pm2;
+          const bool neg_prev = pm1 < 0 || (pm1 == 0 && pm2 > 0);
+          const bool neg_cur = p < 0 || (p == 0 && !neg_prev);
+          cnt += neg_cur != neg_prev;
+          pm2 = pm1; pm1 = p;
+        }
+      }
+    }
+    if (cnt > k) hi = xm; else lo = xm;
+  }
+  return 0.5 * (lo + hi);
+}
+template <int NMAX>
+RB_HD void tridiag_extreme_pair_dyn(const double* d, const double* e, int m, double* hi_out, double* lo_out, bool live) {
+  double lo = d[0], hi = d[0];
+#pragma unroll
+  for (int i = 0; i < NMAX; i++) {
+    if (i < m) {
+      const double r = (i > 0 ? fabs(e[i]) : 0.0) + ((i + 1 < NMAX && i + 1 < m) ? fabs(e[i + 1 < NMAX ? i + 1 : i]) : 0.0);
+      lo = fmin(lo, d[i] - r); hi = fmax(hi, d[i] + r);
+    }
+  }
+  if (m <= 1) { *hi_out = live ? d[0] : 0.0; *lo_out = live ? d[0] : 0.0; return; }
+  double x[2] = {hi + 1e-9, lo - 1e-9};
+  bool done[2] = {!live, !live};
+  const double dm = (double)m;
+  for (int it = 0; it < 24; it++) {
+    if (done[0] && done[1]) break;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      double p0 = 1.0, p1 = d[0] - x[c], q0 = 0.0, q1 = -1.0, r0 = 0.0, r1 = 0.0;   // p, p', p''
+#pragma unroll
+      for (int i = 1; i < NMAX; i++) {
+        if (i < m) {
+          const double a = d[i] - x[c], b = e[i] * e[i];
+          const double p2 = a * p1 - b * p0;
+          const double q2 = a * q1 - p1 - b * q0;
+          const double r2 = a * r1 - 2.0 * q1 - b * r0;
+          p0 = p1; p1 = p2; q0 = q1; q1 = q2; r0 = r1; r1 = r2;
+        }
+      }
+      if (done[c]) continue;
+      if (p1 == 0) { done[c] = true; continue; }
+      const double G = q1 / p1, H = G * G - r1 / p1;
+      const double disc = (dm - 1.0) * (dm * H - G * G);
+      const double sq = sqrt(disc > 0 ? disc : 0.0);
+      const double den = fabs(G + sq) > fabs(G - sq) ? G + sq : G - sq;
+      if (den == 0 || den != den) continue;            // stalls: left to the bisection below
+      const double step = dm / den;
+      x[c] -= step;
+      if (fabs(step) < 1e-10) done[c] = true;
+    }
+  }
+  *hi_out = done[0] ? x[0] : tridiag_bisect_dyn<NMAX>(d, e, m, lo - 1e-9, hi + 1e-9, m - 1);
+  *lo_out = done[1] ? x[1] : tridiag_bisect_dyn<NMAX>(d, e, m, lo - 1e-9, hi + 1e-9, 0);
+  if (!live) { *hi_out = 0; *lo_out = 0; }
+}
 
 // wl: the 27 window levels with the angle axis as the FASTEST coordinate (0 = unmasked / outside);
 // sm: per-thread scratch of LZ_NARR*N doubles with element stride st.
@@ -180,7 +257,7 @@ RB_HD double glcm_lanczos_axis(const int* wl, const TT& T, double* sm, int st, i
 #pragma unroll
   for (int i = 0; i < N - 1; i++) { d[i] = D[(size_t)i * st]; e[i] = E[(size_t)i * st]; }
   double hi, lo;
-  tridiag_extreme_pair_static<N - 1, false>(d, e, &hi, &lo, live);
+  tridiag_extreme_pair_dyn<N - 1>(d, e, n - 1, &hi, &lo, live && n >= 2);      // the deflated space has n - 1 dimensions
   return fmax(fabs(hi), fabs(lo));
 }
 
@@ -209,7 +286,7 @@ RB_HD double glcm_lanczos_task(const uint8_t* w, int ws, const TT& T, int s, dou
 // bipartite (2-colourable; `selfpair` = some level is paired with itself, which rules that out and lets the sweep
 // run with one colour).  A class joins each colour at most once, so the closure loops run <= 2 nlev times in total.
 RB_HD void glcm_graph_scan(const uint32_t* eq, int es, uint32_t EA, int dsh, uint32_t U, bool selfpair, bool* connected,
-                           bool* bipartite) {
+                           bool* bipartite, bool stop_at_odd_cycle = false) {
   const int p0 = RB_CTZ(EA);
   if (selfpair) {
     uint32_t Cm = eq[(size_t)p0 * es], F = Cm;
@@ -231,8 +308,9 @@ RB_HD void glcm_graph_scan(const uint32_t* eq, int es, uint32_t EA, int dsh, uin
     while (PA) { const uint32_t c = eq[(size_t)RB_CTZ(PA) * es]; FB |= c; PA &= ~c; }
     while (PB) { const uint32_t c = eq[(size_t)RB_CTZ(PB) * es]; FA |= c; PB &= ~c; }
     CA |= FA; CB |= FB;
+    if (stop_at_odd_cycle && (CA & CB)) break;   // the caller only wants the colouring: an odd cycle settles it
   }
-  *connected = (U & ~(CA | CB)) == 0;
+  *connected = (U & ~(CA | CB)) == 0;           // (not meaningful after an early stop)
   *bipartite = (CA & CB) == 0;                   // a class that needs both colours closes an odd cycle
 }
 

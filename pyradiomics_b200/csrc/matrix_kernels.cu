@@ -374,7 +374,8 @@ batch_glszm_fill_kernel(const int* __restrict__ zones, const int* __restrict__ n
 // =============================================================================== host drivers
 struct DevBuf {            // RAII for the host-buffer entry points
   void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
+  bool owned = true;       // false: a caller's device buffer (the *_dev entry points borrow the packed level volume)
+  ~DevBuf() { if (p && owned) cudaFree(p); }
   int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : -1; }
   template <typename U> U* as() { return (U*)p; }
 };
@@ -394,8 +395,8 @@ struct Prepared {
 // common front end: shapes, angles, upload + pack (range check), optional voxel list upload
 static int prepare(const int32_t* image, const uint8_t* mask, const int* size, int nd, const int* distances, int ndist,
                    bool bidirectional, int Ng, int force2D, int force2Ddimension, const int* voxels, int nvox,
-                   int kernelRadius, Prepared& R) {
-  if (!image || !mask || !size || (nd != 2 && nd != 3)) return fail(RB_ERR_ARG, "image/mask must be 2-D or 3-D");
+                   int kernelRadius, Prepared& R, const void* levels_dev = nullptr) {
+  if (!size || (nd != 2 && nd != 3)) return fail(RB_ERR_ARG, "image/mask must be 2-D or 3-D");
   if (Ng < 1 || Ng > 65535) return fail(RB_ERR_UNSUPPORTED, "Ng=%d outside 1..65535", Ng);
   if (voxels && kernelRadius <= 0) return fail(RB_ERR_ARG, "Expecting kernelRadius > 0");
   R.nd = nd;
@@ -412,13 +413,19 @@ static int prepare(const int32_t* image, const uint8_t* mask, const int* size, i
     for (int d = 0; d < 3; d++) R.A.a[a][d] = d < 3 - nd ? 0 : (int8_t)R.ang_nd[a * nd + d - (3 - nd)];
   R.lb = Ng <= 255 ? 1 : 2;
   DevBuf dimg, dmsk;
-  if (dimg.alloc(R.n * 4) || dmsk.alloc(R.n) || R.lev.alloc(R.n * R.lb) || R.status.alloc(16))
-    return fail(RB_ERR_NOMEM, "device allocation failed");
-  RB_CUDA(cudaMemcpyAsync(dimg.p, image, R.n * 4, cudaMemcpyHostToDevice, 0));
-  RB_CUDA(cudaMemcpyAsync(dmsk.p, mask, R.n, cudaMemcpyHostToDevice, 0));
+  if (R.status.alloc(16)) return fail(RB_ERR_NOMEM, "device allocation failed");
   RB_CUDA(cudaMemsetAsync(R.status.p, 0, 16, 0));
-  int rc = pack_levels(dimg.as<int32_t>(), dmsk.as<uint8_t>(), R.n, Ng, R.lev.p, nullptr, R.status.as<int>(), 0);
-  if (rc) return rc;
+  if (levels_dev) {                                  // device-resident packed levels (rb_pack_levels_dev), borrowed
+    R.lev.p = const_cast<void*>(levels_dev);
+    R.lev.owned = false;
+  } else {
+    if (!image || !mask) return fail(RB_ERR_ARG, "image/mask must be 2-D or 3-D");
+    if (dimg.alloc(R.n * 4) || dmsk.alloc(R.n) || R.lev.alloc(R.n * R.lb)) return fail(RB_ERR_NOMEM, "device allocation failed");
+    RB_CUDA(cudaMemcpyAsync(dimg.p, image, R.n * 4, cudaMemcpyHostToDevice, 0));
+    RB_CUDA(cudaMemcpyAsync(dmsk.p, mask, R.n, cudaMemcpyHostToDevice, 0));
+    int rc = pack_levels(dimg.as<int32_t>(), dmsk.as<uint8_t>(), R.n, Ng, R.lev.p, nullptr, R.status.as<int>(), 0);
+    if (rc) return rc;
+  }
   if (voxels) {
     if (nvox < 1) return fail(RB_ERR_ARG, "empty voxel list");
     std::vector<int> v3((size_t)3 * nvox, 0);
@@ -468,16 +475,49 @@ static int launch_batch(const Prepared& R, const BatchGeom& G, int Ng, int Nr, i
 }
 
 // one driver for GLCM (mode 0) / GLDM (1) / NGTDM (2) / GLRLM (3)
+int segment_tile_matrices(const uint8_t* lev, int nd, int Z, int Y, int X, const int* distances, int ndist, int Ng, int alpha,
+                          int force2D, int force2Ddimension, double* glcm_host, double* gldm_host, double* ngtdm_host,
+                          int* angles_out, int* na_out, cudaStream_t st);
+int segment_glrlm(const void* lev, int level_bytes, int nd, int Z, int Y, int X, int Ng, int Nr, int force2D, int force2Ddimension,
+                  double* glrlm_host, int* angles_out, int* na_out, cudaStream_t st);
+
+static bool legacy_segment_kernels() {          // B200_SEG_LEGACY=1: round 1's kernels (cross-check in the tests)
+  const char* e = getenv("B200_SEG_LEGACY");
+  return e && e[0] == '1';
+}
+
 int calculate_matrix_host(int mode, const int32_t* image, const uint8_t* mask, const int* size, int nd,
                           const int* distances, int ndist, int Ng, int Nr, int alpha, int force2D, int force2Ddimension,
-                          int kernelRadius, const int* voxels, int nvox, double* out_host, int* angles_out, int* na_out) {
+                          int kernelRadius, const int* voxels, int nvox, double* out_host, int* angles_out, int* na_out,
+                          const void* levels_dev) {
   static const char* names[] = {"GLCM", "GLDM", "NGTDM", "GLRLM"};
   Prepared R;
   const int one[1] = {1};
   const bool bidir = mode == 1 || mode == 2;
   int rc = prepare(image, mask, size, nd, mode == 3 ? one : distances, mode == 3 ? 1 : ndist, bidir, Ng, force2D,
-                   force2Ddimension, voxels, nvox, kernelRadius, R);
+                   force2Ddimension, voxels, nvox, kernelRadius, R, levels_dev);
   if (rc) return rc;
+  if (!voxels && !legacy_segment_kernels()) {
+    // segment mode: the tile-staged fused kernel (8-bit levels, offsets up to 3) / the run-end GLRLM kernel
+    int dmax = 0;
+    for (int i = 0; i < ndist; i++) dmax = distances[i] > dmax ? distances[i] : dmax;
+    if (mode == 3) {
+      rc = segment_glrlm(R.lev.p, R.lb, nd, R.Z, R.Y, R.X, Ng, Nr, force2D, force2Ddimension, out_host, angles_out, na_out, 0);
+      if (rc) return rc;
+      return check_status(R, names[mode]);
+    }
+    if (R.lb == 1 && dmax <= 3) {
+      rc = segment_tile_matrices(R.lev.as<uint8_t>(), nd, R.Z, R.Y, R.X, distances, ndist, Ng, alpha, force2D, force2Ddimension,
+                                 mode == 0 ? out_host : nullptr, mode == 1 ? out_host : nullptr, mode == 2 ? out_host : nullptr,
+                                 nullptr, nullptr, 0);
+      if (rc == RB_OK) {
+        if (na_out) *na_out = R.na;
+        if (angles_out) memcpy(angles_out, R.ang_nd.data(), sizeof(int) * R.ang_nd.size());
+        return check_status(R, names[mode]);
+      }
+      if (rc != RB_ERR_UNSUPPORTED) return rc;        // (too many levels for the shared-memory histograms: round 1's kernels)
+    }
+  }
   if (na_out) *na_out = R.na;
   if (angles_out) memcpy(angles_out, R.ang_nd.data(), sizeof(int) * R.ang_nd.size());
   const int nv = voxels ? nvox : 1;
@@ -557,10 +597,10 @@ struct GlszmHandle {
 
 int glszm_zones_host(const int32_t* image, const uint8_t* mask, const int* size, int nd, int Ng, int force2D,
                      int force2Ddimension, int kernelRadius, const int* voxels, int nvox, int* max_region_out,
-                     void** handle_out) {
+                     void** handle_out, const void* levels_dev) {
   Prepared R;
   const int one[1] = {1};
-  int rc = prepare(image, mask, size, nd, one, 1, true, Ng, force2D, force2Ddimension, voxels, nvox, kernelRadius, R);
+  int rc = prepare(image, mask, size, nd, one, 1, true, Ng, force2D, force2Ddimension, voxels, nvox, kernelRadius, R, levels_dev);
   if (rc) return rc;
   rc = check_status(R, "GLSZM");
   if (rc) return rc;

@@ -123,7 +123,11 @@ struct NgtdmPass1 {
   }
 };
 
-RB_HD void ngtdm_fast_voxel(const int* wl, const SmallFastTables& T, double* out) {
+// scr_pk / scr_cs: per-thread scratch for the compacted level classes, 27 entries each with element stride st (device:
+// shared memory laid out [entry][thread]; round 1 kept them in dynamically indexed local arrays -- 482 M local loads per
+// 256^3 volume, the kernel was as slow as GLRLM for 5 features).  pk = class size << 8 | level, cs = class sum of diff.
+constexpr int NGTDM_SCR_BYTES = 27 * (int)(sizeof(int) + sizeof(double));
+RB_HD void ngtdm_fast_voxel(const int* wl, const SmallFastTables& T, double* out, int* scr_pk, double* scr_cs, int st) {
   uint32_t eq[27];
   RB_EQMASKS_27(wl, eq);
   uint32_t M = 0, rep = 0;
@@ -137,8 +141,6 @@ RB_HD void ngtdm_fast_voxel(const int* wl, const SmallFastTables& T, double* out
   ForPos<0, 27>::go(p1);
   const int Nvp = RB_POPC(M), nlev = RB_POPC(rep);
   // per level: n = class size, i = level, s = class sum of diff -- compacted (data-dependent count)
-  int ln[27], li[27];
-  double lcs[27];
   int B = 0, C = 0, SL = 0, SL2 = 0, nl = 0;
   double ssum = 0, pw = 0;       // sum_i s_i ; sum_i n_i s_i
 #pragma unroll
@@ -147,23 +149,30 @@ RB_HD void ngtdm_fast_voxel(const int* wl, const SmallFastTables& T, double* out
     if (rep >> v & 1u) {
       double s = 0;
 #pragma unroll
-      for (int u = 0; u < 27; u++) if (eq[v] >> u & 1u) s += diff[u];
-      ln[nl] = RB_POPC(eq[v]); li[nl] = wl[v]; lcs[nl] = s; nl++;
+      for (int u = v; u < 27; u++) if (eq[v] >> u & 1u) s += diff[u];      // (v is the lowest position of its class)
+      scr_pk[nl * st] = RB_POPC(eq[v]) << 8 | wl[v];
+      scr_cs[nl * st] = s;
+      nl++;
       SL += wl[v]; SL2 += wl[v] * wl[v];
     }
   }
   // pairwise level terms: Busyness denominator sum_ij |i p_i - j p_j|, Complexity numerator
   double busy = 0, cpx = 0;
-  for (int a = 0; a < nl; a++) {
-    const int na = ln[a], ia = li[a];
-    const double sa = na * lcs[a];
+  for (int a = 0; a + 1 < nl; a++) {
+    const int pa = scr_pk[a * st], na = pa >> 8, ia = pa & 255;
+    const double sa = na * scr_cs[a * st];
+    const int ina = ia * na;
+    double cp = 0;
+    int bs = 0;
     for (int b = a + 1; b < nl; b++) {
-      const int nb_ = ln[b], ib = li[b];
-      const int x = ia * na - ib * nb_;
-      busy += (double)(x < 0 ? -x : x);
+      const int pb = scr_pk[b * st], nb_ = pb >> 8, ib = pb & 255;
+      const int x = ina - ib * nb_;
+      bs += x < 0 ? -x : x;
       const int d = ia > ib ? ia - ib : ib - ia;
-      cpx += (double)d * (sa + nb_ * lcs[b]) * T.rcp[na + nb_];
+      cp += (double)d * (sa + nb_ * scr_cs[b * st]) * T.rcp[na + nb_];
     }
+    busy += (double)bs;
+    cpx += cp;
   }
   const double invN = 1.0 / Nvp;
   busy *= 2.0 * invN;                         // both orders, p = n / Nvp
@@ -178,6 +187,12 @@ RB_HD void ngtdm_fast_voxel(const int* wl, const SmallFastTables& T, double* out
   // Strength = sum_ij (p_i + p_j)(i-j)^2 / sum s = (2/Nvp) (nlev*B - 2*C*SL + Nvp*SL2) / sum s
   const double str = 2.0 * invN * (double)(nlev * B - 2 * C * SL + Nvp * SL2);
   out[N_Strength] = ssum != 0 ? str / ssum : 0.0;
+}
+// convenience: private scratch (host emulation)
+RB_HD void ngtdm_fast_voxel(const int* wl, const SmallFastTables& T, double* out) {
+  int pk[27];
+  double cs[27];
+  ngtdm_fast_voxel(wl, T, out, pk, cs, 1);
 }
 
 // ---------------------------------------------------------------------------------------- GLSZM

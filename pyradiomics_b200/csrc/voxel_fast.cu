@@ -17,7 +17,7 @@
 namespace rb {
 
 #ifndef GF_PHASEA_NT
-#define GF_PHASEA_NT 256
+#define GF_PHASEA_NT 512
 #endif
 
 
@@ -90,8 +90,10 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
     const int zb = za + zchunk < z1 ? za + zchunk : z1;
     const long long total = (long long)(zb - za) * plane;
     RB_CUDA(cudaMemsetAsync(Q->count, 0, sizeof(unsigned), st));
-    // phase A: one CTA per SM (register-bound).  384 threads at 168 registers (a few spilled words) put 12 warps on an
-    // SM instead of the 8 of the 256-thread / 236-register build; B200_GLCM_NT selects the variant for A/B runs.
+    // phase A: one CTA per SM (register-bound).  512 threads at 128 registers (a hundred spilled words per thread, L1-
+    // resident) put 16 warps on an SM instead of the 8 of the 256-thread / 236-register build: measured 50.6 vs 62.5 ms
+    // per 256^3 (uniform), 104.7 vs 117.5 (smooth); 384 threads / 168 registers sit in between.  B200_GLCM_NT selects
+    // the variant for A/B runs.
     static const int nt = getenv("B200_GLCM_NT") ? atoi(getenv("B200_GLCM_NT")) : GF_PHASEA_NT;
     const uint8_t* l8 = (const uint8_t*)lev;
     const long long need = (total + nt - 1) / nt, cap = (long long)sms * 8;
@@ -125,7 +127,10 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
 }
 
 // ---------------------------------------------------------------------------------- GLRLM
-__global__ void __launch_bounds__(128)
+#ifndef GLRLM_MINB
+#define GLRLM_MINB 4
+#endif
+__global__ void __launch_bounds__(128, GLRLM_MINB)
 glrlm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ centers,
                   const __grid_constant__ VoxParams P, const GlrlmFastTables* __restrict__ Tg,
                   double* __restrict__ out, long long fstride, int z0, int z1, int out_z0) {
@@ -218,6 +223,9 @@ small_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ c
                   const __grid_constant__ VoxParams P, const SmallFastTables* __restrict__ Tg,
                   double* __restrict__ out, long long fstride, int z0, int z1, int out_z0) {
   __shared__ SmallFastTables T;
+  // NGTDM: the compacted level classes of every thread, [entry][thread]
+  __shared__ double ng_cs[CLS == C_NGTDM ? 27 * NT : 1];
+  __shared__ int ng_pk[CLS == C_NGTDM ? 27 * NT : 1];
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(Tg);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&T);
@@ -261,7 +269,7 @@ small_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ c
     double f[16];
     if (CLS == C_GLSZM) glszm_fast_voxel(wl, T, f);
     else if (CLS == C_GLDM) gldm_fast_voxel(wl, P.alpha, T, f);
-    else ngtdm_fast_voxel(wl, T, f);
+    else ngtdm_fast_voxel(wl, T, f, ng_pk + (CLS == C_NGTDM ? threadIdx.x : 0), ng_cs + (CLS == C_NGTDM ? threadIdx.x : 0), NT);
     if (!live) continue;
 #pragma unroll
     for (int k = 0; k < NF; k++) out[k * fstride + oi] = is_center ? f[k] : P.init_value;
@@ -317,7 +325,7 @@ int small_fast_launch(int cls, const void* lev, const uint8_t* centers, const Vo
     long long need = (total + 255) / 256, cap = (long long)sms * 16;
     const int grid = (int)(need < cap ? need : cap);
     if (cls == C_GLDM) small_fast_kernel<C_GLDM, 256, true><<<grid, 256, 0, st>>>(l8, centers, P, T, out, fstride, z0, z1, out_z0);
-    else small_fast_kernel<C_NGTDM, 256, true><<<grid, 256, 0, st>>>(l8, centers, P, T, out, fstride, z0, z1, out_z0);
+    else small_fast_kernel<C_NGTDM, 128, true><<<grid * 2, 128, 0, st>>>(l8, centers, P, T, out, fstride, z0, z1, out_z0);   // (its per-thread shared scratch caps the block at 128 threads)
   }
   RB_LAUNCH_CHECK();
   return RB_OK;

@@ -113,6 +113,7 @@ class DeviceImage:
         self._lev32 = lev_t                     # kept until the host copy has been asked for (or never)
         self._binned_host = None
         self._alive = {}
+        self._segment = {}
 
     def binned_host(self):
         """the reference's ``self.imageArray`` after binning: int64 levels, 0 outside the ROI (lazy: voxel mode never needs it)"""
@@ -123,6 +124,14 @@ class DeviceImage:
 
     def levels3d(self):
         return self.levels if self.levels.ndim == 3 else self.levels[None]
+
+    def segment_texture(self, distances, alpha, force2D, force2Ddimension):
+        """GLCM + GLDM + NGTDM of the ROI from ONE pass over the device-resident levels (rb_segment_texture_dev); the three
+        feature classes of one image share the result"""
+        key = (tuple(int(d) for d in distances), int(alpha), bool(force2D), int(force2Ddimension))
+        if key not in self._segment:
+            self._segment[key] = cmatrices.segment_texture_device(self.levels, list(key[0]), max(self.Ng, 1), key[1], key[2], key[3])
+        return self._segment[key]
 
     def glcm_alive(self, settings, centers):
         key = (bytes(settings), None if centers is None else centers.data_ptr())
@@ -182,7 +191,7 @@ class RadiomicsFeaturesBase:
         labelMask = I.as_array(inputMask) == self.label
         if self.voxelBased:
             self.masked = kwargs.get("maskedKernel", True)
-            self.labelledVoxelCoordinates = np.array(np.where(labelMask))
+            self._labelledVoxelCoordinates = None      # lazy: 3 x Nvox int64 (3.2 GB and seconds of np.where at 512^3)
             self._centerMask = labelMask
             self.maskArray = labelMask if self.masked else np.ones(self._rawImageArray.shape, dtype=bool)
         else:
@@ -195,6 +204,14 @@ class RadiomicsFeaturesBase:
         self._device = device_image(self._rawImageArray, self.maskArray, self.settings)
         self.coefficients["grayLevels"] = self._device.grayLevels
         self.coefficients["Ng"] = self._device.Ng
+
+    @property
+    def labelledVoxelCoordinates(self):
+        """the reference's attribute (base.py:98): coordinates of the ROI voxels; built on first use -- the fused kernels
+        take the ROI as a mask volume, nothing on the hot path needs the list"""
+        if getattr(self, "_labelledVoxelCoordinates", None) is None:
+            self._labelledVoxelCoordinates = np.array(np.where(self._centerMask if self.voxelBased else self.maskArray))
+        return self._labelledVoxelCoordinates
 
     @property
     def imageArray(self):
@@ -360,8 +377,11 @@ class RadiomicsGLCM(RadiomicsFeaturesBase):
 
     def _calculateMatrix(self, voxelCoordinates=None):
         f2, f2d = self._matrix_args()
-        P, angles = cmatrices.calculate_glcm(self.imageArray, self.maskArray, np.array(self.settings.get("distances", [1])),
-                                             self.coefficients["Ng"], f2, f2d, *self._batch_args(voxelCoordinates))
+        if voxelCoordinates is None:           # segment mode: the discretised image never leaves the GPU
+            P, angles = self._device.segment_texture(self.settings.get("distances", [1]), self.settings.get("gldm_a", 0), f2, f2d)["glcm"]
+        else:
+            P, angles = cmatrices.calculate_glcm(self.imageArray, self.maskArray, np.array(self.settings.get("distances", [1])),
+                                                 self.coefficients["Ng"], f2, f2d, *self._batch_args(voxelCoordinates))
         w = _weights(angles, self._spacing_zyx(), self.weightingNorm, "glcm")
         # symmetrise / weight / drop the angles that are empty for EVERY voxel of the batch (glcm.py:149-205): one
         # common angle axis, so the batch stacks
@@ -403,8 +423,12 @@ class RadiomicsGLRLM(RadiomicsFeaturesBase):
 
     def _calculateMatrix(self, voxelCoordinates=None):
         f2, f2d = self._matrix_args()
-        P, angles = cmatrices.calculate_glrlm(self.imageArray, self.maskArray, self.coefficients["Ng"],
-                                              int(np.max(self.imageArray.shape)), f2, f2d, *self._batch_args(voxelCoordinates))
+        if voxelCoordinates is None:
+            P, angles = cmatrices.calculate_glrlm_device(self._device.levels, self.coefficients["Ng"],
+                                                         int(np.max(self._rawImageArray.shape)), f2, f2d)
+        else:
+            P, angles = cmatrices.calculate_glrlm(self.imageArray, self.maskArray, self.coefficients["Ng"],
+                                                  int(np.max(self.imageArray.shape)), f2, f2d, *self._batch_args(voxelCoordinates))
         w = _weights(angles, self._spacing_zyx(), self.weightingNorm, "glrlm")
         if P.shape[0] != 1:
             raise NotImplementedError("P_glrlm of a voxel batch: the voxel-based path is fused (no per-voxel matrices); "
@@ -438,8 +462,11 @@ class RadiomicsGLSZM(_SizeMatrixClass):
 
     def _calculateMatrix(self, voxelCoordinates=None):
         f2, f2d = self._matrix_args()
-        P = cmatrices.calculate_glszm(self.imageArray, self.maskArray, self.coefficients["Ng"], int(np.sum(self.maskArray)),
-                                      f2, f2d, *self._batch_args(voxelCoordinates))
+        if voxelCoordinates is None:
+            P = cmatrices.calculate_glszm_device(self._device.levels, self.coefficients["Ng"], f2, f2d)
+        else:
+            P = cmatrices.calculate_glszm(self.imageArray, self.maskArray, self.coefficients["Ng"], int(np.sum(self.maskArray)),
+                                          f2, f2d, *self._batch_args(voxelCoordinates))
         if P.shape[0] != 1:
             raise NotImplementedError("P_glszm of a voxel batch: use cmatrices.calculate_glszm for dense per-voxel matrices")
         M, j = MF.size_matrix_process(P[0], self.coefficients["grayLevels"])
@@ -460,8 +487,11 @@ class RadiomicsGLDM(_SizeMatrixClass):
 
     def _calculateMatrix(self, voxelCoordinates=None):
         f2, f2d = self._matrix_args()
-        P = cmatrices.calculate_gldm(self.imageArray, self.maskArray, np.array(self.settings.get("distances", [1])),
-                                     self.coefficients["Ng"], self.gldm_a, f2, f2d, *self._batch_args(voxelCoordinates))
+        if voxelCoordinates is None:
+            P = self._device.segment_texture(self.settings.get("distances", [1]), self.gldm_a, f2, f2d)["gldm"]
+        else:
+            P = cmatrices.calculate_gldm(self.imageArray, self.maskArray, np.array(self.settings.get("distances", [1])),
+                                         self.coefficients["Ng"], self.gldm_a, f2, f2d, *self._batch_args(voxelCoordinates))
         if P.shape[0] != 1:
             raise NotImplementedError("P_gldm of a voxel batch: use cmatrices.calculate_gldm for dense per-voxel matrices")
         M, j = MF.size_matrix_process(P[0], self.coefficients["grayLevels"])
@@ -480,8 +510,11 @@ class RadiomicsNGTDM(RadiomicsFeaturesBase):
 
     def _calculateMatrix(self, voxelCoordinates=None):
         f2, f2d = self._matrix_args()
-        P = cmatrices.calculate_ngtdm(self.imageArray, self.maskArray, np.array(self.settings.get("distances", [1])),
-                                      self.coefficients["Ng"], f2, f2d, *self._batch_args(voxelCoordinates))
+        if voxelCoordinates is None:
+            P = self._device.segment_texture(self.settings.get("distances", [1]), self.settings.get("gldm_a", 0), f2, f2d)["ngtdm"]
+        else:
+            P = cmatrices.calculate_ngtdm(self.imageArray, self.maskArray, np.array(self.settings.get("distances", [1])),
+                                          self.coefficients["Ng"], f2, f2d, *self._batch_args(voxelCoordinates))
         keep = P[:, :, 0].sum(0) != 0
         return P[:, keep]
 
@@ -519,8 +552,12 @@ class RadiomicsFirstOrder(RadiomicsFeaturesBase):
         r = int(self.settings.get("kernelRadius", 1))
         nd = self._raw.ndim
         if self.masked:
-            idx = self.labelledVoxelCoordinates
-            size = idx.max(1) - idx.min(1) + 1
+            m = self._centerMask
+            size = []
+            for d in range(m.ndim):
+                on = np.flatnonzero(m.any(axis=tuple(k for k in range(m.ndim) if k != d)))
+                size.append(int(on[-1] - on[0] + 1))
+            size = np.array(size)
         else:
             size = np.array(self._raw.shape)
         rad = [int(min(r, s - 1)) for s in size]

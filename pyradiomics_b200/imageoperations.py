@@ -110,9 +110,13 @@ def getBinEdges(parameterValues, **kwargs):
     return _edges_from_minmax(mn, mx, _NP_OF_TORCH[t.dtype], **kwargs)
 
 
-def bin_image_device(img_t: torch.Tensor, mask_t: torch.Tensor | None, **kwargs):
-    """device tensors in -> (int32 levels tensor (0 outside the mask), edges ndarray)."""
+def bin_image_device(img_t: torch.Tensor, mask_t: torch.Tensor | None, minmax_reduce=None, **kwargs):
+    """device tensors in -> (int32 levels tensor (0 outside the mask), edges ndarray).  `minmax_reduce(mn, mx)` turns a
+    slab's ROI minimum / maximum into the whole ROI's (multi-GPU: all-reduce MIN / MAX), so every rank bins with the
+    same edges."""
     mn, mx, _ = roi_minmax(img_t, mask_t)
+    if minmax_reduce is not None:
+        mn, mx = minmax_reduce(mn, mx)
     edges_native = _edges_from_minmax(mn, mx, _NP_OF_TORCH[img_t.dtype], **kwargs)
     edges = np.ascontiguousarray(edges_native, dtype=np.float64)
     e_t = torch.from_numpy(edges).to(img_t.device)
@@ -179,12 +183,27 @@ def wavelet_filters(name):
     return lo, hi
 
 
-def swt_level1_device(x: torch.Tensor, axes, lo, hi):
-    """one undecimated level over `axes` (in that order) of a float64 CUDA volume (Z,Y,X):
-    {'aad': tensor, ...} with one letter per axis in `axes` order, like pywt.swtn."""
+def swt_level1_device(x: torch.Tensor, axes, lo, hi, z_range=None):
+    """one undecimated level over `axes` (in that order) of a float64 CUDA volume (Z,Y,X), periodic extension:
+    {'aad': tensor, ...} with one letter per axis in `axes` order, like pywt.swtn.  Three axes with a 2/4/6/8-tap
+    filter take the fused single-pass kernel (rb_swt3d_dev); anything else runs one axis per pass."""
     Z, Y, X = x.shape
     lo = np.ascontiguousarray(lo, dtype=np.float64)
     hi = np.ascontiguousarray(hi, dtype=np.float64)
+    axes = [int(a) for a in axes]
+    if sorted(axes) == [0, 1, 2] and lo.size in (2, 4, 6, 8):
+        x = x.contiguous()
+        zb, ze = (0, Z) if z_range is None else (int(z_range[0]), int(z_range[1]))      # slab + halo in, interior planes out
+        out = torch.empty((8, ze - zb, Y, X), dtype=torch.float64, device=x.device)
+        check(lib().rb_swt3d_dev(_ptr(x), Z, Y, X, lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), int(lo.size),
+                                 _ptr(out), C.c_longlong(out.stride(0)), zb, ze, _stream()), "swt3d")
+        res = {}
+        for b in range(8):
+            band = {2: b & 1, 1: b >> 1 & 1, 0: b >> 2 & 1}          # axis (0 = z, 1 = y, 2 = x) -> high-pass?
+            res["".join("d" if band[a] else "a" for a in axes)] = out[b]
+        return res
+    if z_range is not None:
+        raise ValueError("z_range needs the fused 3-D kernel (three axes, 2/4/6/8 taps)")
     cur = {"": x}
     for ax in axes:
         nxt = {}
@@ -198,7 +217,20 @@ def swt_level1_device(x: torch.Tensor, axes, lo, hi):
     return cur
 
 
+def _wrap_pad_even(data: torch.Tensor, axes3):
+    """reference imageoperations.py:914-919: every transformed axis of odd length gets ONE wrap-around sample appended;
+    returns the padded tensor and the crop slices that undo it (:947-951, :961-963)"""
+    crop = [slice(None)] * 3
+    for ax in axes3:
+        if data.shape[ax] % 2:
+            crop[ax] = slice(0, data.shape[ax])
+            data = torch.cat([data, data.narrow(ax, 0, 1)], dim=ax)
+    return data.contiguous(), tuple(crop)
+
+
 def _swt3(inputImage, axes, **kwargs):
+    """reference _swt3 (imageoperations.py:899-970): pad ONCE, keep the padded approximation between the levels (each
+    level is a level-1 transform of the previous approximation), crop only what is handed out"""
     wavelet = kwargs.get("wavelet", "coif1")
     level = kwargs.get("level", 1)
     start_level = kwargs.get("start_level", 0)
@@ -209,20 +241,22 @@ def _swt3(inputImage, axes, **kwargs):
     if nd == 2:
         data = data[None]
     ax3 = [a + (3 - nd) for a in axes]
+    data, crop = _wrap_pad_even(data, ax3)
+    key_a = "a" * len(axes)
     for _ in range(start_level):
-        data = swt_level1_device(data, ax3, lo, hi)["a" * len(axes)]
+        data = swt_level1_device(data, ax3, lo, hi)[key_a]
     ret = []
     for _ in range(start_level, start_level + level):
         dec = swt_level1_device(data, ax3, lo, hi)
-        data = dec["a" * len(axes)]
+        data = dec[key_a]
         dec_im = {}
         for name, t in dec.items():
-            if name == "a" * len(axes):
+            if name == key_a:
                 continue
-            a = t.cpu().numpy()
+            a = t[crop].cpu().numpy()
             dec_im[name.replace("a", "L").replace("d", "H")] = I.like(inputImage, a[0] if nd == 2 else a)
         ret.append(dec_im)
-    a = data.cpu().numpy()
+    a = data[crop].cpu().numpy()
     return I.like(inputImage, a[0] if nd == 2 else a), ret
 
 
@@ -289,29 +323,39 @@ def recursive_gaussian_coefficients(sigmad: float, order: int, scale_norm: float
     return np.concatenate([N, D, M, BN, BM]).astype(np.float64)
 
 
-def log_filter_device(x: torch.Tensor, sigma_mm: float, spacing_zyx):
-    """sigma^2-normalised Laplacian of Gaussian of a CUDA volume (Z,Y,X) -> float32 tensor."""
-    Z, Y, X = x.shape
-    src = x.to(torch.float32) if x.dtype != torch.float64 else x
-    scratch = torch.empty((Z, Y, X), dtype=torch.float64, device=x.device)
-    out = torch.zeros((Z, Y, X), dtype=torch.float32, device=x.device)
-    tmp = [torch.empty((Z, Y, X), dtype=torch.float32, device=x.device) for _ in range(2)]
-    for d in range(3):
-        cur, cur_f32 = src, src.dtype == torch.float32
-        k = 0
-        for e in range(3):
-            if e == d:
-                continue
-            coef = recursive_gaussian_coefficients(sigma_mm / spacing_zyx[e], 0)
-            check(lib().rb_recursive_gaussian_axis_dev(_ptr(cur), int(cur_f32), Z, Y, X, e, coef.ctypes.data_as(C.c_void_p),
-                                                       _ptr(tmp[k]), _ptr(scratch), C.c_double(1.0), 0, _stream()), "LoG")
-            cur, cur_f32 = tmp[k], True
-            k ^= 1
-        sd = sigma_mm / spacing_zyx[d]
-        coef = recursive_gaussian_coefficients(sd, 2)
-        # sigma^2 * d^2/dx^2 in physical units = (sigma/spacing)^2 * d^2/di^2
-        check(lib().rb_recursive_gaussian_axis_dev(_ptr(cur), 1, Z, Y, X, d, coef.ctypes.data_as(C.c_void_p), _ptr(out),
-                                                   _ptr(scratch), C.c_double(sd * sd), 1, _stream()), "LoG")
+def _rg_pass(src: torch.Tensor, axis: int, sigma_vox: float, order: int, out: torch.Tensor | None = None, scale: float = 1.0,
+             accumulate: bool = False):
+    """one recursive-Gaussian axis pass (order 0 = smoothing, 2 = second derivative) of a float32 / float64 CUDA volume
+    into a float32 volume"""
+    Z, Y, X = src.shape
+    if out is None:
+        out = torch.empty((Z, Y, X), dtype=torch.float32, device=src.device)
+    scratch = torch.empty((Z, Y, X), dtype=torch.float64, device=src.device)
+    coef = recursive_gaussian_coefficients(sigma_vox, order)
+    check(lib().rb_recursive_gaussian_axis_dev(_ptr(src), int(src.dtype == torch.float32), Z, Y, X, int(axis),
+                                               coef.ctypes.data_as(C.c_void_p), _ptr(out), _ptr(scratch), C.c_double(scale),
+                                               int(accumulate), _stream()), "LoG")
+    return out
+
+
+def log_filter_device(x: torch.Tensor, sigma_mm: float, spacing_zyx, z_pass=None):
+    """sigma^2-normalised Laplacian of Gaussian of a CUDA volume (Z,Y,X) -> float32 tensor: for each direction d,
+    Gaussian smoothing along the other two axes (z first) then the second derivative along d, summed over d (ITK's
+    LaplacianRecursiveGaussianImageFilter, reference radiomics/imageoperations.py:824-830).
+    `z_pass(src, sigma_vox, order, scale)` replaces the pass along z: a multi-GPU caller holding a z-slab transposes to
+    y-slabs, runs the scan over the whole lines there and transposes back (pipeline.derived_images_slab); every other
+    pass is local to the slab, so the distributed result is bit-identical to the single-GPU one."""
+    src = x.to(torch.float32).contiguous() if x.dtype != torch.float64 else x.contiguous()
+    sz, sy, sx = (sigma_mm / spacing_zyx[0], sigma_mm / spacing_zyx[1], sigma_mm / spacing_zyx[2])
+    if z_pass is None:
+        z_pass = lambda t, sv, order, scale: _rg_pass(t, 0, sv, order, scale=scale)
+    # d = z: smooth y, x; derivative z
+    cur = _rg_pass(_rg_pass(src, 1, sy, 0), 2, sx, 0)
+    out = z_pass(cur, sz, 2, sz * sz)
+    # d = y and d = x both start with the smoothing along z of the input
+    gz = z_pass(src, sz, 0, 1.0)
+    _rg_pass(_rg_pass(gz, 2, sx, 0), 1, sy, 2, out=out, scale=sy * sy, accumulate=True)      # + sigma^2 d2/dy2
+    _rg_pass(_rg_pass(gz, 1, sy, 0), 2, sx, 2, out=out, scale=sx * sx, accumulate=True)      # + sigma^2 d2/dx2
     return out
 
 

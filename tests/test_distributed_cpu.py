@@ -63,3 +63,48 @@ def test_slab_ranges_cover_volume():
             rs = [D.slab_range(Z, k, world) for k in range(world)]
             assert rs[0][0] == 0 and rs[-1][1] == Z
             assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+
+
+def _worker_filters(rank, world, port, Z, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(11)
+    Y, X = 7, 5
+    vol = rng.normal(size=(Z, Y, X))
+    z0, z1 = D.slab_range(Z, rank, world)
+    # periodic asymmetric halo (coif1: 2 planes below, 3 above), ring closed between rank 0 and rank world-1
+    slab = D.SlabHalo(torch.from_numpy(vol[z0:z1].copy()), 2, rank, world, hi=3, periodic=True)
+    slab.exchange()
+    exp = np.stack([vol[k % Z] for k in range(z0 - 2, z1 + 3)])
+    ok = np.array_equal(slab.buf.numpy(), exp)
+    # z-slab -> y-slab -> z-slab
+    ys = D.zslab_to_yslab(torch.from_numpy(vol[z0:z1].copy()), Z, rank, world)
+    y0, y1 = D.slab_range(Y, rank, world)
+    ok = ok and np.array_equal(ys.numpy(), vol[:, y0:y1, :])
+    back = D.yslab_to_zslab(ys, Y, rank, world)
+    ok = ok and np.array_equal(back.numpy(), vol[z0:z1])
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,Z", [(2, 8), (2, 11), (3, 13)])
+def test_periodic_halo_ring_and_slab_transposition(world, Z):
+    """multi-GPU pre-filters: the wavelet's ring-closed 2+3-plane halo and the LoG z pass's transposition"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_filters, args=(k, world, port, Z, q)) for k in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
+
+
+def test_periodic_halo_single_rank():
+    vol = torch.arange(6 * 2 * 2, dtype=torch.float64).reshape(6, 2, 2)
+    s = D.SlabHalo(vol, 2, 0, 1, hi=3, periodic=True)
+    s.exchange()
+    assert torch.equal(s.buf, torch.stack([vol[k % 6] for k in range(-2, 9)]))

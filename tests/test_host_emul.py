@@ -267,6 +267,9 @@ def test_eigen_task_solvers_against_lapack(emul):
                 assert nout.value == n
                 if n > 12:
                     assert lz == d                                          # layout-independent, same code as the dispatcher
+                for N2 in (16, 18):                                         # a larger size template: the SAME bits
+                    if N2 > N:
+                        assert emul.emul_glcm_lanczos_axis(wp.ctypes.data_as(C.c_void_p), N2, 1, 0, C.byref(nout)) == lz
                 worst["lanczos_small"] = max(worst["lanczos_small"], abs(lz - ref)); count["lanczos_small"] += 1
     assert count["dense"] > 3000 and count["lanczos"] > 150 and count["lanczos_small"] > 1000, count
     assert worst["dense"] < 1e-9, worst
@@ -310,3 +313,36 @@ def test_phaseA_graph_scan_against_bruteforce(emul):
             assert bool(r & 1) == bip, (w, a)
         seen[(int(conn), int(bip and conn))] += 1
     assert seen[(1, 1)] > 100 and seen[(1, 0)] > 500 and seen[(0, 0)] > 500, seen
+
+
+@pytest.mark.parametrize("kind", ["uniform", "smooth"])
+def test_glrlm_glszm_gldm_ngtdm_fast_math_equals_generic_math_on_host(emul, kind):
+    """the r=1 bitmask fast paths (csrc/glrlm_fast.cuh, small_fast.cuh) against the generic entry-list kernels' math on a
+    22^3 volume with holes (ragged windows, dropped GLRLM angles)"""
+    rng = np.random.default_rng(3)
+    shape = (22, 22, 22)
+    if kind == "uniform":
+        lev = rng.integers(1, 33, shape)
+        lev[rng.random(shape) < 0.1] = 0
+    else:
+        zz, yy, xx = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
+        f = np.sin(zz / 2.7) + np.cos(yy / 3.1) + np.sin(xx / 2.3 + 1) + 0.25 * rng.normal(size=shape)
+        lev = np.digitize(f, np.quantile(f, np.linspace(0, 1, 33)[1:-1])) + 1
+        lev[5:9, 3:20, 7] = 0
+        lev[12, :, :] = 0                         # a plane of holes: windows that lose whole GLRLM angles
+    lev = np.ascontiguousarray(lev, dtype=np.uint16)
+    s = _lib.make_settings(32, 32)
+    Zs, Ys, Xs = shape
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for cid, cname in enumerate(_lib.CLASSES):
+        if cname == "glcm":
+            continue
+        nf = len(NAMES[cname])
+        fast, gen = np.zeros((nf, Zs, Ys, Xs)), np.zeros((nf, Zs, Ys, Xs))
+        if cname == "glrlm":
+            assert emul.emul_glrlm_fast(p(lev), Zs, Ys, Xs, C.byref(s), p(fast)) == 0
+        else:
+            assert emul.emul_small_fast(cid, p(lev), Zs, Ys, Xs, C.byref(s), p(fast)) == 0
+        assert emul.emul_voxel_features(cid, p(lev), None, Zs, Ys, Xs, C.byref(s), None, p(gen)) == 0
+        for k, f in enumerate(NAMES[cname]):
+            assert np.allclose(fast[k], gen[k], rtol=1e-10, atol=1e-12, equal_nan=True), (cname, f, np.nanmax(np.abs(fast[k] - gen[k])))

@@ -142,3 +142,54 @@ def test_segment_mode_at_scale_properties():
     assert D.sum() == N ** 3
     Z = B.calculate_glszm(img, msk, 32, N ** 3, False, 0)
     assert (Z[0] * np.arange(1, Z.shape[2] + 1)[None, :]).sum() == N ** 3
+
+
+# ---- round 2: tile-staged fused segment kernel (TMA / cooperative), run-end GLRLM, device-resident entry points
+@pytest.mark.parametrize("shape,dist", [((20, 33, 64), [1]), ((9, 17, 48), [1, 2]), ((1, 40, 80), [1]), ((37, 29, 23), [1, 3])])
+def test_segment_kernels_tma_equals_cooperative_equals_legacy(shape, dist, monkeypatch):
+    """the fused GLCM + GLDM + NGTDM tile kernel with its box staged by TMA (row pitch a multiple of 16 bytes) or by
+    cooperative loads, and the run-end GLRLM kernel, against round 1's one-thread-per-voxel kernels: identical matrices"""
+    import torch
+    from pyradiomics_b200 import cmatrices, voxel
+    rng = np.random.default_rng(12)
+    if shape[0] == 1:
+        shape = shape[1:]
+    lev = rng.integers(1, 25, shape).astype(np.int32)
+    msk = rng.random(shape) < 0.8
+    res = {}
+    for mode in ("tma", "coop", "legacy"):
+        monkeypatch.setenv("B200_SEG_TMA", "0" if mode == "coop" else "1")
+        monkeypatch.setenv("B200_SEG_LEGACY", "1" if mode == "legacy" else "0")
+        P, ang = cmatrices.calculate_glcm(lev, msk, dist, 24, False, -1)
+        R, _ = cmatrices.calculate_glrlm(lev, msk, 24, max(shape), False, -1)
+        res[mode] = (P, cmatrices.calculate_gldm(lev, msk, dist, 24, 1, False, -1), cmatrices.calculate_ngtdm(lev, msk, dist, 24, False, -1), R)
+    for k in range(4):
+        assert np.array_equal(res["tma"][k], res["coop"][k])
+        if k == 2:      # s_i is an fp64 sum: exact-integer accumulation in both, same division order -> still identical
+            assert np.allclose(res["tma"][k], res["legacy"][k], rtol=1e-14, atol=0)
+        else:
+            assert np.array_equal(res["tma"][k], res["legacy"][k])
+    # the same from a device-resident packed level volume, all three matrices in one pass
+    monkeypatch.setenv("B200_SEG_TMA", "1")
+    monkeypatch.setenv("B200_SEG_LEGACY", "0")
+    levd, _ = voxel.pack_levels(torch.as_tensor(lev).cuda(), torch.as_tensor(msk).cuda(), 24)
+    d = cmatrices.segment_texture_device(levd, dist, 24, 1, False, -1)
+    assert np.array_equal(d["glcm"][0], res["tma"][0]) and np.array_equal(d["gldm"], res["tma"][1]) and np.array_equal(d["ngtdm"], res["tma"][2])
+    Rd, _ = cmatrices.calculate_glrlm_device(levd, 24, max(shape), False, -1)
+    assert np.array_equal(Rd, res["tma"][3])
+    Zd = cmatrices.calculate_glszm_device(levd, 24, False, -1)
+    assert np.array_equal(Zd, cmatrices.calculate_glszm(lev, msk, 24, int(msk.sum()), False, -1))
+
+
+def test_glrlm_single_voxel_lines_rule_from_pigeonhole_counts():
+    """cmatrices.c:524-534: an angle none of whose lines holds two masked voxels loses its run-length-1 column"""
+    import cmatrices_oracle as O
+    from pyradiomics_b200 import cmatrices
+    lev = np.zeros((5, 6, 7), np.int32)
+    msk = np.zeros(lev.shape, bool)
+    for (z, y, x, g) in [(0, 0, 0, 3), (2, 3, 4, 5), (4, 1, 6, 2), (1, 5, 2, 7)]:      # isolated voxels: most angles have no 2-voxel line
+        lev[z, y, x] = g; msk[z, y, x] = True
+    lev[2, 3, 5] = 5; msk[2, 3, 5] = True                                              # one x-neighbour pair
+    got, ang = cmatrices.calculate_glrlm(lev, msk, 8, 7, False, -1)
+    ref, ang_r = O.calculate_glrlm(lev, msk, 8, 7, False, -1)
+    assert np.array_equal(ang, ang_r) and np.array_equal(got, ref)

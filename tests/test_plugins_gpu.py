@@ -337,3 +337,94 @@ def test_host_extractor_float32_and_float64_agree():
     b = voxel.HostExtractor(lev.shape, zchunk=7, out_dtype=torch.float32).run(lev, msk, 32, 32)
     for c in a:
         assert torch.equal(a[c].to(torch.float32), b[c]) or torch.allclose(a[c].to(torch.float32), b[c], equal_nan=True, rtol=0, atol=0)
+
+
+# ------------------------------------------------------------------------------ wavelet: phase, levels, odd sizes (round 2)
+@pytest.mark.parametrize("shape", [(12, 10, 16), (9, 11, 13)])
+def test_wavelet_impulse_response_is_the_filter_taps_at_the_documented_phase(shape):
+    """out[n] = sum_j h[j] x[(n + F/2 - j) mod N]  =>  an impulse at p puts tap h[j] at p - F/2 + j (periodic), separably
+    for all 8 bands; first band letter <-> x (the LAST numpy axis: the reference passes axes = (2,1,0))"""
+    lo, hi = IO.wavelet_filters("coif1")
+    F = lo.size
+    p = (4, 5, 6)
+    x = np.zeros(shape)
+    x[p] = 1.0
+    got = {n: I.as_array(im) for im, n, _ in IO.getWaveletImage(I.ArrayImage(x), None)}
+    pads = [s + (s % 2) for s in shape]
+
+    def line(h, n_axis, n_pad, pos):
+        v = np.zeros(n_pad)
+        for j in range(F):
+            v[(pos - F // 2 + j) % n_pad] += h[j]
+        return v[:n_axis]
+
+    for name, arr in got.items():
+        letters = name.split("-")[1]                       # x, y, z
+        fx, fy, fz = [(hi if c == "H" else lo) for c in letters]
+        ref = np.einsum("i,j,k->ijk", line(fz, shape[0], pads[0], p[0]), line(fy, shape[1], pads[1], p[1]),
+                        line(fx, shape[2], pads[2], p[2]))
+        assert np.allclose(arr, ref, rtol=0, atol=1e-15), name
+
+
+@pytest.mark.parametrize("shape,kw", [((9, 11, 13), dict(level=2)), ((8, 9, 10), dict(level=2, start_level=1)),
+                                      ((10, 12, 14), dict(level=3)), ((7, 9), dict(level=2))])
+def test_wavelet_levels_keep_the_padded_approximation_like_the_reference(shape, kw):
+    """_swt3 pads ONCE and feeds the padded approximation to the next level (imageoperations.py:917-937): for odd sizes
+    level >= 2 differs from re-wrapping a cropped approximation (round 1 did the latter)"""
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=shape)
+    lo, hi = IO.wavelet_filters("coif1")
+    nd = len(shape)
+    axes = tuple(range(nd - 1, -1, -1))
+    approx, levels = FN.swt3_levels(x, lo, hi, axes, kw.get("level", 1), kw.get("start_level", 0))
+    got = {n: I.as_array(im) for im, n, _ in IO.getWaveletImage(I.ArrayImage(x), None, **kw)}
+    assert len(got) == len(levels) * (2 ** nd - 1) + 1
+    for idx, dec in enumerate(levels, start=1):
+        for key, arr in dec.items():
+            band = key.replace("a", "L").replace("d", "H")
+            name = f"wavelet-{band}" if idx == 1 else f"wavelet{idx}-{band}"
+            assert np.allclose(got[name], arr, rtol=1e-12, atol=1e-12), name
+    last = f"wavelet-{'L' * nd}" if len(levels) == 1 else f"wavelet{len(levels)}-{'L' * nd}"
+    assert np.allclose(got[last], approx, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("wavelet", ["haar", "db2", "coif1"])
+def test_fused_3d_wavelet_kernel_equals_axis_by_axis_kernel(wavelet):
+    lo, hi = IO.wavelet_filters(wavelet)
+    x = torch.randn((20, 37, 70), dtype=torch.float64, device="cuda")           # tiles with ragged edges in y and x
+    fused = IO.swt_level1_device(x, (2, 1, 0), lo, hi)
+    cur = {"": x}
+    for ax in (2, 1, 0):
+        nxt = {}
+        for k, t in cur.items():
+            a, d = torch.empty_like(t), torch.empty_like(t)
+            import ctypes as C
+            from pyradiomics_b200._lib import check, lib
+            check(lib().rb_swt_axis_dev(C.c_void_p(t.data_ptr()), 20, 37, 70, ax, lo.ctypes.data_as(C.c_void_p),
+                                        hi.ctypes.data_as(C.c_void_p), int(lo.size), C.c_void_p(a.data_ptr()), C.c_void_p(d.data_ptr()),
+                                        None), "swt")
+            nxt[k + "a"], nxt[k + "d"] = a, d
+        cur = nxt
+    # (37 is odd: the axis kernel wrap-pads by index mapping, the fused kernel is purely periodic -> compare on an even copy too)
+    xe = x[:, :36].contiguous()
+    fe = IO.swt_level1_device(xe, (2, 1, 0), lo, hi)
+    ref = FN.swtn_level1(xe.cpu().numpy(), lo, hi, (2, 1, 0))
+    for k in ref:
+        assert np.allclose(fe[k].cpu().numpy(), ref[k], rtol=1e-12, atol=1e-12), k
+    assert set(fused) == set(cur)
+
+
+def test_log_x_axis_tiles_match_restatement_on_ragged_sizes():
+    """the shared-memory-transposed x pass: line counts and lengths that are not multiples of 32"""
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(5, 7, 45)).astype(np.float32) * 50
+    out = [I.as_array(im) for im, n, _ in IO.getLoGImage(I.ArrayImage(x, (1.0, 1.0, 1.0)), None, sigma=[1.5])][0]
+    ref = np.zeros(x.shape)
+    xf = x.astype(np.float64)
+    for d in range(3):
+        cur = xf
+        for e in range(3):
+            if e != d:
+                cur = FN.recursive_gaussian_axis(cur, IO.recursive_gaussian_coefficients(1.5, 0), e).astype(np.float32).astype(np.float64)
+        ref += (FN.recursive_gaussian_axis(cur, IO.recursive_gaussian_coefficients(1.5, 2), d) * 1.5 ** 2).astype(np.float32)
+    assert np.allclose(out, ref, rtol=2e-4, atol=2e-4 * np.abs(ref).max())

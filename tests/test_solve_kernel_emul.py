@@ -39,10 +39,9 @@ def test_emulated_solve_kernels_process_every_task_once(kind, n):
     rk, rd, cls = rk[:nt], rd[:nt], cls[:nt]
     assert not (rk == -12345.0).any(), "a queued task was not picked up by any solve kernel"
     assert not np.isnan(rk).any()
-    dense = cls <= 10
-    assert np.array_equal(rk[dense], rd[dense])         # same code, same inputs: bit-identical to the direct solve
-    # large tasks may be topped up into a batch of the next larger Lanczos size (padded nodes): same value to rounding
-    assert np.allclose(rk[~dense], rd[~dense], rtol=0, atol=1e-12)
+    # bit-identical to the direct solve -- also for the large tasks that were topped up into a batch of the next larger
+    # Lanczos size template (padded nodes add exact zeros; the eigenvalue search is sized by the task, not the template)
+    assert np.array_equal(rk, rd)
     hist = np.bincount(cls, minlength=16)
     assert hist[:7].sum() and hist[7:11].sum() and hist[11:].sum()      # all three kernels had work
 
@@ -72,7 +71,4 @@ def test_emulated_glcm_pipeline_equals_per_voxel_math(kind, n):
     lev16 = lev.astype(np.uint16)
     assert emul.emul_glcm_fast(p(lev16), n, n, n, C.byref(s), None, p(ref)) == 0
     for k, name in enumerate(_lib.feature_names("glcm")):
-        if name == "MCC":              # Lanczos tasks may run in a larger size class than the single-thread composition picks
-            assert np.allclose(out[k], ref[k], rtol=0, atol=1e-12, equal_nan=True), name
-        else:
-            assert np.array_equal(out[k], ref[k], equal_nan=True), name
+        assert np.array_equal(out[k], ref[k], equal_nan=True), name
