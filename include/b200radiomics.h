@@ -214,6 +214,19 @@ int rb_recursive_gaussian_axis_dev(const void *in_dev, int in_is_f32, int Z, int
                                    const double *coef20, float *out_dev, double *scratch_dev, double scale,
                                    int accumulate, void *stream);
 
+/* ---- resampling onto the extraction grid (reference radiomics/imageoperations.py:448-612:
+ *      sitk.ResampleImageFilter, sitkBSpline for the image, sitkNearestNeighbor for the mask, axis-aligned grids).
+ * rb_bspline_prefilter_dev: in-place cubic B-spline coefficients of a float64 volume (ITK BSplineDecompositionImageFilter:
+ *   pole sqrt(3)-2, mirror boundaries, x then y then z).
+ * rb_resample_dev: dst[o] = interpolate(src, start + o * step) for every output voxel o (z,y,x); `interpolator` 0 = nearest
+ *   neighbour, 1 = linear, 3 = cubic B-spline (src = the float64 coefficients); `default_value` outside the input buffer
+ *   (continuous index outside [-0.5, size-0.5)); the result is clamped to the range of dst_dtype and TRUNCATED like ITK's
+ *   cast.  dtype codes as rb_minmax_dev. */
+int rb_bspline_prefilter_dev(double *coeffs_dev, int Z, int Y, int X, void *stream);
+int rb_resample_dev(const void *src_dev, int src_dtype, const int *in_size_zyx, void *dst_dev, int dst_dtype,
+                    const int *out_size_zyx, const double *start_zyx, const double *step_zyx, int interpolator,
+                    double default_value, void *stream);
+
 /* ---- segment-mode shape coefficients ------------------------------
  * rb_calculate_coefficients replaces calculate_coefficients (radiomics/src/cshape.h:1-2, binding
  *   radiomics/src/_cshape.c:75-113): HOST mask (non-zero = ROI) of `size` = {Z, Y, X} with element
@@ -229,6 +242,12 @@ int rb_calculate_coefficients(const char *mask, const int *size, const int *stri
 int rb_shape_coefficients_dev(const uint8_t *mask_dev, int Z, int Y, int X, const double *spacing_zyx,
                               double *out7, void *stream);
 int rb_shape_moments_dev(const uint8_t *mask_dev, int Z, int Y, int X, unsigned long long *out10, void *stream);
+/* rb_calculate_coefficients2D replaces calculate_coefficients2D (radiomics/src/cshape.h, cshape.c:420-595, binding
+ *   radiomics/src/_cshape.c:33-39 used by radiomics/shape2D.py:99): HOST mask of `size` = {Y, X} with element `strides`,
+ *   `spacing` = {y, x}: marching-squares perimeter and surface of the ROI outline and the maximum diameter over its
+ *   vertices (bit-identical to the reference's; perimeter / surface differ by summation order only). */
+int rb_calculate_coefficients2D(const char *mask, const int *size, const int *strides, const double *spacing,
+                                double *perimeter, double *surface, double *diameter);
 
 /* ---- voxel-based first-order feature maps (the next plugin after the five
  *      texture classes; reference radiomics/firstorder.py:40-474).  For every centre voxel of planes

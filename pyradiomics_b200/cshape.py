@@ -16,8 +16,7 @@ _fallback = None        # the reference's _cshape module, set by featureclasses.
 
 
 def __getattr__(name):
-    """names this module does not implement (calculate_coefficients2D: reference radiomics/src/_cshape.c:33-39,
-    used by radiomics/shape2D.py:99) are served by the reference's own extension when install() found one"""
+    """names this module does not implement are served by the reference's own extension when install() found one"""
     if _fallback is not None and hasattr(_fallback, name):
         return getattr(_fallback, name)
     raise AttributeError(f"module 'pyradiomics_b200.cshape' has no attribute {name!r}")
@@ -41,6 +40,26 @@ def calculate_coefficients(mask, pixelSpacing):
     if rc:
         check(rc, "Calculation of Shape coefficients failed.")
     return sa.value, vol.value, tuple(dia)
+
+
+def calculate_coefficients2D(mask, pixelSpacing):
+    """(Perimeter, Surface, MaximumDiameter) of a 2-D mask: drop-in for the reference's
+    ``cShape.calculate_coefficients2D`` (radiomics/src/_cshape.c:33-39, cshape.c:420-595; called at shape2D.py:99)"""
+    msk = np.ascontiguousarray(np.asarray(mask).astype(np.int8, copy=False))
+    sp = np.ascontiguousarray(np.asarray(pixelSpacing).astype(np.float64, copy=False))
+    if msk.ndim != 2:
+        raise ValueError("Expected a 2D array for mask")
+    if sp.ndim != 1 or sp.shape[0] != 2:
+        raise ValueError("Expecting spacing array to have shape (2,)")
+    size = np.array(msk.shape, dtype=np.int32)
+    strides = np.array([s // msk.itemsize for s in msk.strides], dtype=np.int32)
+    per, sur, dia = C.c_double(), C.c_double(), C.c_double()
+    rc = lib().rb_calculate_coefficients2D(msk.ctypes.data_as(C.c_char_p), size.ctypes.data_as(C.c_void_p),
+                                           strides.ctypes.data_as(C.c_void_p), sp.ctypes.data_as(C.c_void_p),
+                                           C.byref(per), C.byref(sur), C.byref(dia))
+    if rc:
+        check(rc, "Calculation of Shape coefficients failed.")
+    return per.value, sur.value, dia.value
 
 
 def coefficients_device(mask_t, spacing_zyx):

@@ -65,6 +65,8 @@ int minmax_launch(const void* img, int dt, const uint8_t* mask, long long n, lon
 int shape_coefficients_dev(const uint8_t* mask_dev, int Z, int Y, int X, long long sz, long long sy, long long sx,
                            const double* spacing, double* out7, cudaStream_t st);
 int shape_moments_dev(const uint8_t* mask_dev, int Z, int Y, int X, unsigned long long* out10, cudaStream_t st);
+int shape2d_coefficients_dev(const uint8_t* mask_dev, int Y, int X, long long sy, long long sx, const double* spacing, double* out4,
+                             cudaStream_t st);
 int digitize_launch(const void* img, int dt, const uint8_t* mask, long long n, const double* edges, int ne, int32_t* out,
                     cudaStream_t st);
 int swt_axis_launch(const double* in, int Z, int Y, int X, int axis, const double* lo, const double* hi, int F,
@@ -73,6 +75,9 @@ int recursive_gauss_launch(const void* in, int in_is_f32, int Z, int Y, int X, i
                            double* scratch, double scale, int accumulate, cudaStream_t st);
 int swt3d_launch(const double* in, int Z, int Y, int X, const double* lo, const double* hi, int F, double* out,
                  long long band_stride, int z_begin, int z_end, cudaStream_t st);
+int bspline_prefilter_launch(double* coeffs, int Z, int Y, int X, cudaStream_t st);
+int resample_launch(const void* src, int src_dt, const int* in_size, void* dst, int dst_dt, const int* out_size, const double* start,
+                    const double* step, int interp, double default_value, cudaStream_t st);
 
 int firstorder_launch(const void* img, int dtype, const uint8_t* mask, const uint8_t* centers, const void* lev,
                       int level_bytes, int Z, int Y, int X, int rz, int ry, int rx, double shift, double voxel_volume,
@@ -331,6 +336,16 @@ int rb_swt_axis_dev(const double* in_dev, int Z, int Y, int X, int axis, const d
   if (axis < 0 || axis > 2) return fail(RB_ERR_ARG, "axis must be 0..2");
   return swt_axis_launch(in_dev, Z, Y, X, axis, dec_lo, dec_hi, flen, out_lo_dev, out_hi_dev, (cudaStream_t)stream);
 }
+int rb_bspline_prefilter_dev(double* coeffs_dev, int Z, int Y, int X, void* stream) {
+  return bspline_prefilter_launch(coeffs_dev, Z, Y, X, (cudaStream_t)stream);
+}
+int rb_resample_dev(const void* src_dev, int src_dtype, const int* in_size_zyx, void* dst_dev, int dst_dtype, const int* out_size_zyx,
+                    const double* start_zyx, const double* step_zyx, int interpolator, double default_value, void* stream) {
+  if (!src_dev || !dst_dev || !in_size_zyx || !out_size_zyx || !start_zyx || !step_zyx) return fail(RB_ERR_ARG, "null argument");
+  return resample_launch(src_dev, src_dtype, in_size_zyx, dst_dev, dst_dtype, out_size_zyx, start_zyx, step_zyx, interpolator,
+                         default_value, (cudaStream_t)stream);
+}
+
 int rb_swt3d_dev(const double* in_dev, int Z, int Y, int X, const double* dec_lo, const double* dec_hi, int flen,
                  double* out_dev, long long band_stride, int z_begin, int z_end, void* stream) {
   return swt3d_launch(in_dev, Z, Y, X, dec_lo, dec_hi, flen, out_dev, band_stride, z_begin, z_end, (cudaStream_t)stream);
@@ -373,6 +388,27 @@ int rb_calculate_coefficients(const char* mask, const int* size, const int* stri
   if (rc) return rc;
   *surfaceArea = out7[0]; *volume = out7[1];
   for (int q = 0; q < 4; q++) diameters[q] = out7[2 + q];
+  return RB_OK;
+}
+
+int rb_calculate_coefficients2D(const char* mask, const int* size, const int* strides, const double* spacing, double* perimeter,
+                                double* surface, double* diameter) {
+  if (!mask || !size || !strides || !spacing || !perimeter || !surface || !diameter) return fail(RB_ERR_ARG, "null argument");
+  const int Y = size[0], X = size[1];
+  if (Y < 1 || X < 1) return fail(RB_ERR_ARG, "empty mask");
+  // gather the (possibly strided) host mask into a contiguous byte image, then one upload
+  std::vector<uint8_t> h((size_t)Y * X);
+  for (int y = 0; y < Y; y++)
+    for (int x = 0; x < X; x++) h[(size_t)y * X + x] = mask[(long long)y * strides[0] + (long long)x * strides[1]] != 0;
+  uint8_t* d = NULL;
+  RB_CUDA(cudaMalloc(&d, h.size()));
+  cudaError_t e = cudaMemcpy(d, h.data(), h.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d); return fail(RB_ERR_CUDA, "shape2D upload: %s", cudaGetErrorString(e)); }
+  double out4[4];
+  const int rc = shape2d_coefficients_dev(d, Y, X, X, 1, spacing, out4, 0);
+  cudaFree(d);
+  if (rc) return rc;
+  *perimeter = out4[0]; *surface = out4[1]; *diameter = out4[2];
   return RB_OK;
 }
 

@@ -257,10 +257,11 @@ static int sm_count() {
   return sms;
 }
 
-// B200_SEG_TMA=0 forces the cooperative-load staging (A/B runs, tests)
+// B200_SEG_TMA=1 selects the TMA staging, 0 / unset the cooperative loads (see DESIGN.md section 3.2 for why the
+// default is the cooperative path on this pool's boxes)
 static bool seg_tma_enabled() {
   const char* e = getenv("B200_SEG_TMA");
-  return !(e && e[0] == '0');
+  return e && e[0] == '1';
 }
 
 // GLCM (flag 1) / GLDM (2) / NGTDM (4) of one packed uint8 level volume in one pass; outputs are HOST float64 buffers in

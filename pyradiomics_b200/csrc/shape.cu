@@ -248,4 +248,126 @@ int shape_moments_dev(const uint8_t* mask_dev, int Z, int Y, int X, unsigned lon
   return RB_OK;
 }
 
+// ---- 2-D shape coefficients (reference radiomics/src/cshape.c:420-595: calculate_coefficients2D + calculate_meshDiameter2D)
+// Marching squares with edge-midpoint vertices over every 2x2 neighbourhood of the (zero-padded) mask.  What the reference
+// gets from a 16-entry line table is stated geometrically here: a square with 1 or 3 inside corners is cut by ONE corner
+// segment (length sqrt((sy/2)^2 + (sx/2)^2), inside area 1/8 or 7/8 of the pixel), two adjacent inside corners by a
+// straight segment (length sx or sy, area 1/2), and the two diagonal cases by TWO corner segments that keep the inside
+// corners apart (area 2/8; probed on the compiled reference: [[1,0],[0,1]] has surface 1.0).  The signed-triangle sum
+// of the reference equals that area by Green's theorem; summing positive per-square areas instead avoids its cancellation.
+// Mesh vertices for the diameter = midpoints of the crossed LEFT and BOTTOM square edges (each crossed grid edge once).
+struct Shape2DAcc { double perimeter, area8; unsigned long long nverts; };
+
+__global__ void __launch_bounds__(256)
+shape2d_kernel(const uint8_t* __restrict__ mask, int Y, int X, long long sy_, long long sx_, double spy, double spx,
+               Shape2DAcc* __restrict__ acc, ushort2* __restrict__ verts, unsigned long long* __restrict__ cursor) {
+  const long long n = (long long)(Y - 1) * (X - 1);
+  const double diag = sqrt(0.25 * spy * spy + 0.25 * spx * spx);
+  double per = 0;
+  long long a8 = 0;
+  unsigned nv = 0;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int iy = (int)(t / (X - 1)), ix = (int)(t % (X - 1));
+    const bool p0 = mask[iy * sy_ + ix * sx_] != 0, p1 = mask[iy * sy_ + (ix + 1) * sx_] != 0;
+    const bool p3 = mask[(iy + 1) * sy_ + ix * sx_] != 0, p2 = mask[(iy + 1) * sy_ + (ix + 1) * sx_] != 0;
+    const int cnt = p0 + p1 + p2 + p3;
+    if (cnt == 0 || cnt == 4) { if (cnt == 4) a8 += 8; continue; }
+    if (cnt == 1) { per += diag; a8 += 1; }
+    else if (cnt == 3) { per += diag; a8 += 7; }
+    else if (p0 == p2) { per += diag + diag; a8 += 2; }                 // diagonal pair: two separate corner cuts
+    else { per += (p0 == p1) ? spx : spy; a8 += 4; }                    // top/bottom rows split: the cut runs along x
+    // crossed left edge (p0 | p3) and bottom edge (p3 - p2): stored in half-index units (2*iy+1, 2*ix) / (2*iy+2, 2*ix+1)
+    if (verts) {
+      if (p0 != p3) verts[atomicAdd(cursor, 1ull)] = make_ushort2((unsigned short)(2 * iy + 1), (unsigned short)(2 * ix));
+      if (p3 != p2) verts[atomicAdd(cursor, 1ull)] = make_ushort2((unsigned short)(2 * iy + 2), (unsigned short)(2 * ix + 1));
+    } else {
+      nv += (p0 != p3) + (p3 != p2);
+    }
+  }
+  __shared__ double rp[256];
+  __shared__ long long ra[256];
+  __shared__ unsigned rn[256];
+  rp[threadIdx.x] = per; ra[threadIdx.x] = a8; rn[threadIdx.x] = nv;
+  __syncthreads();
+  for (int h = 128; h > 0; h >>= 1) {
+    if ((int)threadIdx.x < h) { rp[threadIdx.x] += rp[threadIdx.x + h]; ra[threadIdx.x] += ra[threadIdx.x + h]; rn[threadIdx.x] += rn[threadIdx.x + h]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && !verts) {
+    if (rp[0] != 0) atomicAdd(&acc->perimeter, rp[0]);
+    if (ra[0]) atomicAdd(&acc->area8, (double)ra[0]);            // eighths of a pixel: exact in double
+    if (rn[0]) atomicAdd(&acc->nverts, (unsigned long long)rn[0]);
+  }
+}
+
+// largest squared distance over all vertex pairs; coordinates and products formed exactly like the reference
+// ((index + offset) * spacing, difference, square, sum -- no FMA contraction), so the maximum is bit-identical
+__global__ void __launch_bounds__(256)
+shape2d_diameter_kernel(const ushort2* __restrict__ verts, long long n, double spy, double spx, unsigned long long* __restrict__ best) {
+  __shared__ double ty[256], tx[256];
+  double mx = 0;
+  for (long long i0 = (long long)blockIdx.x * 256; i0 < n; i0 += (long long)gridDim.x * 256) {
+    const long long i = i0 + threadIdx.x;
+    const bool live = i < n;
+    const ushort2 vi = verts[live ? i : 0];
+    const double ay = __dmul_rn(0.5 * vi.x, spy), ax = __dmul_rn(0.5 * vi.y, spx);
+    for (long long j0 = 0; j0 <= i0; j0 += 256) {
+      __syncthreads();
+      const long long j = j0 + threadIdx.x;
+      const ushort2 vj = verts[j < n ? j : 0];
+      ty[threadIdx.x] = __dmul_rn(0.5 * vj.x, spy); tx[threadIdx.x] = __dmul_rn(0.5 * vj.y, spx);
+      __syncthreads();
+      const int lim = (int)((n - j0) < 256 ? (n - j0) : 256);
+      if (live)
+        for (int k = 0; k < lim; k++) {
+          const double dy = __dsub_rn(ay, ty[k]), dx = __dsub_rn(ax, tx[k]);
+          const double d2 = __dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dx, dx));
+          mx = d2 > mx ? d2 : mx;
+        }
+    }
+  }
+  for (int o = 16; o; o >>= 1) { const double v = __shfl_xor_sync(0xffffffffu, mx, o); mx = v > mx ? v : mx; }
+  if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(best, (unsigned long long)__double_as_longlong(mx));   // positive doubles order like integers
+}
+
+// mask_dev: uint8 [Y][X] with element strides (sy, sx) -- already zero-padded by the caller like the reference does
+// (shape2D.py:93); out4 (host) = perimeter, surface, maximum diameter, number of mesh vertices
+int shape2d_coefficients_dev(const uint8_t* mask_dev, int Y, int X, long long sy, long long sx, const double* spacing, double* out4,
+                             cudaStream_t st) {
+  for (int k = 0; k < 4; k++) out4[k] = 0;
+  if (Y < 2 || X < 2) return RB_OK;
+  if (Y > 32767 || X > 32767) return fail(RB_ERR_ARG, "shape2D: dimensions above 32767 are not supported");
+  struct Dev { Shape2DAcc acc; unsigned long long cursor, best; };
+  Dev* d = nullptr;
+  RB_CUDA(cudaMalloc(&d, sizeof(Dev)));
+  cudaMemsetAsync(d, 0, sizeof(Dev), st);
+  const long long nsq = (long long)(Y - 1) * (X - 1);
+  const int grid = grid_for(nsq, 256, 8);
+  shape2d_kernel<<<grid, 256, 0, st>>>(mask_dev, Y, X, sy, sx, spacing[0], spacing[1], &d->acc, nullptr, nullptr);
+  Dev h;
+  cudaError_t e = cudaMemcpyAsync(&h, d, sizeof(Dev), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { cudaFree(d); return fail(RB_ERR_CUDA, "shape2D pass: %s", cudaGetErrorString(e)); }
+  out4[0] = h.acc.perimeter;
+  out4[1] = h.acc.area8 * 0.125 * spacing[0] * spacing[1];
+  out4[3] = (double)h.acc.nverts;
+  if (h.acc.nverts) {
+    ushort2* verts = nullptr;
+    e = cudaMalloc(&verts, sizeof(ushort2) * h.acc.nverts);
+    if (e != cudaSuccess) { cudaFree(d); return fail(RB_ERR_NOMEM, "shape2D: %llu vertices do not fit", h.acc.nverts); }
+    shape2d_kernel<<<grid, 256, 0, st>>>(mask_dev, Y, X, sy, sx, spacing[0], spacing[1], &d->acc, verts, &d->cursor);
+    const long long nt = ((long long)h.acc.nverts + 255) / 256;
+    shape2d_diameter_kernel<<<(int)(nt < 148 * 8 ? nt : 148 * 8), 256, 0, st>>>(verts, (long long)h.acc.nverts, spacing[0], spacing[1], &d->best);
+    e = cudaMemcpyAsync(&h, d, sizeof(Dev), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(verts);
+    if (e != cudaSuccess) { cudaFree(d); return fail(RB_ERR_CUDA, "shape2D diameter pass: %s", cudaGetErrorString(e)); }
+    double v;
+    memcpy(&v, &h.best, 8);
+    out4[2] = sqrt(v);
+  }
+  cudaFree(d);
+  return RB_OK;
+}
+
 }  // namespace rb

@@ -127,10 +127,7 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
 }
 
 // ---------------------------------------------------------------------------------- GLRLM
-#ifndef GLRLM_MINB
-#define GLRLM_MINB 4
-#endif
-__global__ void __launch_bounds__(128, GLRLM_MINB)
+__global__ void __launch_bounds__(128)
 glrlm_fast_kernel(const uint8_t* __restrict__ lev, const uint8_t* __restrict__ centers,
                   const __grid_constant__ VoxParams P, const GlrlmFastTables* __restrict__ Tg,
                   double* __restrict__ out, long long fstride, int z0, int z1, int out_z0) {

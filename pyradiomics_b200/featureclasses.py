@@ -700,10 +700,87 @@ def _add_shape_getters():
 
 _add_shape_getters()
 
+class RadiomicsShape2D(RadiomicsFeaturesBase):
+    """2-D shape descriptors of a single-slice ROI (reference radiomics/shape2D.py): perimeter, mesh surface and maximum
+    diameter from the CUDA marching-squares + all-pairs kernels (rb_calculate_coefficients2D), axis lengths from the pixel
+    covariance.  Segment-based only; needs a 2-D mask or a 3-D one with force2D and size 1 in force2Ddimension."""
+    CLASS, MATRIX_ATTR = "shape2D", "_unused_matrix"
+    NAMES = ["MeshSurface", "PixelSurface", "Perimeter", "PerimeterSurfaceRatio", "Sphericity", "MaximumDiameter",
+             "MajorAxisLength", "MinorAxisLength", "Elongation"]
+    DEPRECATED = ["SphericalDisproportion"]
+
+    def __init__(self, inputImage, inputMask, **kwargs):
+        if kwargs.get("voxelBased", False):
+            raise NotImplementedError("Shape features are not available in pixel-based mode")
+        super().__init__(inputImage, inputMask, **kwargs)
+
+    def _initBinning(self):                   # shape ignores intensities
+        self._imageArray = self._rawImageArray
+
+    def _calculateVoxels(self):
+        raise NotImplementedError("Shape features are not available in pixel-based mode")
+
+    def _initCalculation(self, voxelCoordinates=None):
+        from . import cshape
+        m = np.asarray(self.maskArray, dtype=bool)
+        sp = np.array(self._spacing_zyx(), dtype=np.float64)
+        if m.ndim == 3:                       # shape2D.py:62-84
+            if not self.settings.get("force2D", False):
+                raise ValueError("Shape2D is can only be calculated when input is 2D or 3D with `force2D=True`")
+            d = self.settings.get("force2Ddimension", 0)
+            if m.shape[d] > 1:
+                raise ValueError("Size of the mask in dimension %i is more than 1, cannot compute 2D shape" % d)
+            m = np.squeeze(m, axis=d)
+            sp = np.delete(sp, d)
+        elif m.ndim != 2:
+            raise ValueError("Shape2D is can only be calculated when input is 2D or 3D with `force2D=True`")
+        self.pixelSpacing = sp
+        padded = np.pad(m, 1)
+        self.Perimeter, self.Surface, self.Diameter = cshape.calculate_coefficients2D(padded, sp)
+        idx = np.array(np.where(padded), dtype=np.float64).T
+        self._Np = len(idx)
+        phys = idx * sp[None, :]
+        phys -= phys.mean(0)
+        phys /= np.sqrt(self._Np)
+        ev = np.linalg.eigvals(phys.T.copy() @ phys).real
+        ev[(ev < 0) & (ev > -1e-10)] = 0
+        self.eigenValues = np.sort(ev)
+
+    def _segment_features(self):
+        ev = self.eigenValues
+        with np.errstate(divide="ignore", invalid="ignore"):
+            sph = (2 * np.sqrt(np.pi * self.Surface)) / self.Perimeter
+            f = {"MeshSurface": self.Surface, "PixelSurface": self._Np * float(np.multiply.reduce(self.pixelSpacing)),
+                 "Perimeter": self.Perimeter, "PerimeterSurfaceRatio": self.Perimeter / self.Surface, "Sphericity": sph,
+                 "SphericalDisproportion": 1.0 / sph, "MaximumDiameter": self.Diameter,
+                 "MajorAxisLength": np.nan if ev[1] < 0 else np.sqrt(ev[1]) * 4,
+                 "MinorAxisLength": np.nan if ev[0] < 0 else np.sqrt(ev[0]) * 4,
+                 "Elongation": np.nan if (ev[0] < 0 or ev[1] < 0) else np.sqrt(ev[0] / ev[1])}
+        return f
+
+    def _value(self, name):
+        if not hasattr(self, "Surface"):
+            self._initCalculation()
+        return np.float64(self._segment_features()[name])
+
+
+def _add_shape2d_getters():
+    _add_feature_getters(RadiomicsShape2D, RadiomicsShape2D.NAMES)
+    for n in RadiomicsShape2D.DEPRECATED:
+        def getter(self, _n=n):
+            return self._value(_n)
+        getter.__name__ = f"get{n}FeatureValue"
+        getter.__doc__ = f"SHAPE2D {n} (deprecated in the reference: the inverse of Sphericity)."
+        getter._is_deprecated = True
+        setattr(RadiomicsShape2D, getter.__name__, getter)
+
+
+_add_shape2d_getters()
+
 FEATURE_CLASSES = {"glcm": RadiomicsGLCM, "glrlm": RadiomicsGLRLM, "glszm": RadiomicsGLSZM, "gldm": RadiomicsGLDM,
                    "ngtdm": RadiomicsNGTDM}
 # next row of the hot-path table (SURVEY.md section 8f): registered by install() as well
-NEXT_CLASSES = {"firstorder": RadiomicsFirstOrder, "shape": RadiomicsShape}
+NEXT_CLASSES = {"firstorder": RadiomicsFirstOrder, "shape": RadiomicsShape, "shape2D": RadiomicsShape2D}
 
 
 def install(radiomics_module=None):
@@ -724,7 +801,7 @@ def install(radiomics_module=None):
     if orig is not None and orig is not cshape and getattr(orig, "__name__", "") != cshape.__name__:
         cshape._fallback = orig
     rad.cShape = cshape
-    for mod in ("shape",):
+    for mod in ("shape", "shape2D"):
         try:
             importlib.import_module(f"{rad.__name__}.{mod}").cShape = cshape
         except ImportError:

@@ -17,10 +17,14 @@ except ImportError:  # pragma: no cover
 class ArrayImage:
     """(z,y,x) NumPy array + spacing in SimpleITK (x,y,z) order."""
 
-    def __init__(self, array, spacing=None):
+    def __init__(self, array, spacing=None, origin=None):
         self.array = np.asarray(array)
         nd = self.array.ndim
         self.spacing = tuple(float(s) for s in (spacing if spacing is not None else (1.0,) * nd))
+        self.origin = tuple(float(o) for o in (origin if origin is not None else (0.0,) * nd))
+
+    def GetOrigin(self):
+        return self.origin
 
     def GetSize(self):
         return tuple(int(s) for s in self.array.shape[::-1])
@@ -33,6 +37,8 @@ class ArrayImage:
 
     def CopyInformation(self, other):
         self.spacing = tuple(other.GetSpacing())
+        if hasattr(other, "GetOrigin"):
+            self.origin = tuple(other.GetOrigin())
 
 
 def as_array(img):
@@ -53,6 +59,12 @@ def spacing_xyz(img):
     return tuple(img.GetSpacing())
 
 
+def origin_xyz(img):
+    if isinstance(img, np.ndarray) or not hasattr(img, "GetOrigin"):
+        return (0.0,) * np.ndim(as_array(img))
+    return tuple(img.GetOrigin())
+
+
 def size_xyz(img):
     return tuple(int(s) for s in as_array(img).shape[::-1])
 
@@ -63,4 +75,4 @@ def like(ref, array):
         out = _sitk.GetImageFromArray(array)
         out.CopyInformation(ref)
         return out
-    return ArrayImage(array, spacing_xyz(ref))
+    return ArrayImage(array, spacing_xyz(ref), origin_xyz(ref))

@@ -160,6 +160,97 @@ def cropToTumorMask(imageNode, maskNode, boundingBox, **kwargs):
     return I.like(imageNode, I.as_array(imageNode)[sl]), I.like(maskNode, I.as_array(maskNode)[sl])
 
 
+# ------------------------------------------------------------------------------------ resampling
+_INTERPOLATORS = {"sitkNearestNeighbor": 0, "sitkLinear": 1, "sitkBSpline": 3, 1: 0, 2: 1, 3: 3}      # (sitk enum values 1, 2, 3)
+_NP_DT = {np.dtype("int16"): 0, np.dtype("int32"): 1, np.dtype("float32"): 2, np.dtype("float64"): 3, np.dtype("uint8"): 4,
+          np.dtype("int64"): 6}
+
+
+def resample_device(arr_t: torch.Tensor, out_size_zyx, start_zyx, step_zyx, interpolator=3, default_value=0.0, out_dtype=None):
+    """CUDA tensor (Z,Y,X) -> CUDA tensor of `out_size_zyx` sampled at input continuous indices start + k * step
+    (rb_bspline_prefilter_dev + rb_resample_dev); cubic B-spline (3), linear (1) or nearest neighbour (0); the result is
+    clamped and truncated to `out_dtype` (default: the input's) like ITK's ResampleImageFilter"""
+    src = arr_t.contiguous()
+    out_dtype = out_dtype or src.dtype
+    if out_dtype not in _TORCH_DT:
+        raise ValueError(f"unsupported pixel type {out_dtype}")
+    Z, Y, X = src.shape
+    dst = torch.empty(tuple(int(v) for v in out_size_zyx), dtype=out_dtype, device=src.device)
+    if interpolator == 3:
+        src = src.to(torch.float64).clone()
+        check(lib().rb_bspline_prefilter_dev(_ptr(src), Z, Y, X, _stream()), "bspline prefilter")
+    elif src.dtype not in _TORCH_DT:
+        src = src.to(torch.float64)
+    isz = (C.c_int * 3)(Z, Y, X)
+    osz = (C.c_int * 3)(*[int(v) for v in out_size_zyx])
+    st = (C.c_double * 3)(*[float(v) for v in start_zyx])
+    sp = (C.c_double * 3)(*[float(v) for v in step_zyx])
+    check(lib().rb_resample_dev(_ptr(src), _TORCH_DT[src.dtype], isz, _ptr(dst), _TORCH_DT[out_dtype], osz, st, sp, int(interpolator),
+                                C.c_double(float(default_value)), _stream()), "resample")
+    return dst
+
+
+def resampleImage(imageNode, maskNode, **kwargs):
+    """reference signature (radiomics/imageoperations.py:448-612): resample image (B-spline by default) and mask (nearest
+    neighbour) to `resampledPixelSpacing`, cropped to the ROI's bounding box grown by `padDistance` new-grid voxels; the
+    grid is aligned to the input origin.  The geometry arithmetic is the reference's (:509-566); image and mask are taken
+    to share one axis-aligned grid (the array stand-in of SimpleITK images carries spacing and origin, no direction
+    cosines).  Interpolation and cast happen on the GPU (resample_device)."""
+    resampledPixelSpacing = kwargs["resampledPixelSpacing"]
+    interpolator = kwargs.get("interpolator", "sitkBSpline")
+    padDistance = kwargs.get("padDistance", 5)
+    label = int(kwargs.get("label", 1))
+    if imageNode is None or maskNode is None:
+        raise ValueError("Requires both image and mask to resample")
+    img, msk = I.as_array(imageNode), I.as_array(maskNode)
+    if img.shape != msk.shape:
+        raise ValueError("image and mask must share one grid")
+    nd = msk.ndim
+    maskSpacing = np.array(I.spacing_xyz(maskNode), dtype=np.float64)
+    assert len(resampledPixelSpacing) == nd, f"Wrong dimensionality ({len(resampledPixelSpacing)}-D) of resampledPixelSpacing!, {nd}-D required"
+    newSp = np.array(resampledPixelSpacing, dtype=np.float64)
+    newSp = np.where(newSp == 0, maskSpacing, newSp)
+    # bounding box (lower bounds then sizes, x,y,z) of the label: what LabelShapeStatisticsImageFilter gives _checkROI (:346-404)
+    idx = np.array(np.where(msk == label))
+    if idx.shape[1] == 0:
+        raise ValueError(f"Label ({label}) not present in mask")
+    lo, hi = idx.min(1)[::-1], idx.max(1)[::-1]
+    bb = np.concatenate([lo, hi - lo + 1]).astype(np.float64)
+    maskSize = np.array(msk.shape[::-1], dtype=np.float64)
+    newSp = np.where(bb[nd:] != 1, newSp, maskSpacing)                  # no resampling across a single-slice ROI (:509-511)
+    if np.allclose(maskSpacing, newSp):                                  # nothing to interpolate: crop only (:517-537)
+        low_up = np.empty(nd * 2, dtype=int)
+        low_up[::2], low_up[1::2] = lo, hi
+        return cropToTumorMask(imageNode, maskNode, low_up, **kwargs)
+    ratio = maskSpacing / newSp
+    L = np.floor((bb[:nd] - 0.5) * ratio - padDistance)
+    U = np.ceil((bb[:nd] + bb[nd:] - 0.5) * ratio + padDistance)
+    maxU = np.ceil(maskSize * ratio) - 1
+    L = np.where(L < 0, 0, L)
+    U = np.where(U > maxU, maxU, U)
+    newSize = np.array(U - L + 1, dtype=int)
+    start = 0.5 * (newSp - maskSpacing) / maskSpacing + L / ratio       # continuous index of output voxel 0 (:549-556)
+    step = newSp / maskSpacing
+    if isinstance(interpolator, str) and interpolator not in _INTERPOLATORS:
+        logger.warning('interpolator "%s" not recognized, using sitkBSpline', interpolator)
+        interpolator = "sitkBSpline"
+    if interpolator not in _INTERPOLATORS:
+        raise ValueError(f"interpolator {interpolator!r} is not implemented (sitkBSpline, sitkLinear, sitkNearestNeighbor)")
+    logger.info("Applying resampling from spacing %s and size %s to spacing %s and size %s", maskSpacing, maskSize, newSp, newSize)
+    pad3 = (1,) * (3 - nd)
+    img_t = _to_device(img).reshape(pad3 + img.shape)
+    msk_t = _to_device(msk).reshape(pad3 + msk.shape)
+    osz = pad3 + tuple(int(v) for v in newSize[::-1])
+    st3 = (0.0,) * (3 - nd) + tuple(start[::-1])
+    sp3 = (1.0,) * (3 - nd) + tuple(step[::-1])
+    out_img = resample_device(img_t, osz, st3, sp3, _INTERPOLATORS[interpolator])
+    out_msk = resample_device(msk_t, osz, st3, sp3, 0)
+    origin = np.array(I.origin_xyz(maskNode), dtype=np.float64) + start * maskSpacing      # TransformContinuousIndexToPhysicalPoint (:557)
+    a_img = out_img.cpu().numpy().reshape(osz[3 - nd:]).astype(img.dtype, copy=False)
+    a_msk = out_msk.cpu().numpy().reshape(osz[3 - nd:]).astype(msk.dtype if msk.dtype != np.bool_ else np.uint8, copy=False)
+    return I.ArrayImage(a_img, tuple(newSp), tuple(origin)), I.ArrayImage(a_msk, tuple(newSp), tuple(origin))
+
+
 # ------------------------------------------------------------------------------------ wavelet
 # decomposition low-pass filters (PyWavelets conventions); dec_hi[k] = (-1)^(k+1) dec_lo[F-1-k]
 _DEC_LO = {

@@ -244,3 +244,37 @@ class HostExtractor:
         self.copy_stream.synchronize()
         torch.cuda.current_stream(self.dev).synchronize()
         return self.h_out
+
+
+def extract_to_nrrd(lev: torch.Tensor, settings, out_dir, classes=CLASSES, prefix="original", spacing_xyz=(1.0, 1.0, 1.0),
+                    origin_xyz=(0.0, 0.0, 0.0), compress=True, level=1, workers=8, out_dtype=torch.float64, centers=None,
+                    zchunk=64, features=None):
+    """Voxel driver + output assembly in one pipeline (the reference: extractor.execute(..., voxelBased=True) then one
+    sitk.WriteImage(map, target, True) per map, radiomics/scripts/voxel.py:62-72): the fused kernels of one class stream
+    their maps chunk by chunk into page-locked host memory (class_maps_to_host) while a pool of writer threads gzips the
+    PREVIOUS class's maps into <prefix>_<class>_<Feature>.nrrd files (zlib releases the GIL), so compression and disk
+    overlap the GPU and the PCIe stream.  `features` = {class: [names]} restricts what is copied and written.
+    Returns {feature key: path}."""
+    import concurrent.futures as cf
+    import os
+
+    from . import nrrd
+    os.makedirs(out_dir, exist_ok=True)
+    jobs, keep = {}, []
+    copy_stream = torch.cuda.Stream(device=lev.device)
+    with cf.ThreadPoolExecutor(max_workers=max(1, int(workers))) as ex:
+        for c in [c for c in HostExtractor.ORDER if c in classes]:
+            names = _lib.feature_names(c)
+            want = names if not features or c not in features else [n for n in names if n in set(features[c])]
+            idx = [names.index(n) for n in want]
+            if not idx:
+                continue
+            host = class_maps_to_host(c, lev, settings, idx, centers=centers, zchunk=zchunk, out_dtype=out_dtype,
+                                      copy_stream=copy_stream, sync=True)
+            keep.append(host)
+            arr = host.numpy()
+            for pos, n in enumerate(want):
+                key = f"{prefix}_{c}_{n}"
+                jobs[key] = ex.submit(nrrd.write_nrrd, os.path.join(out_dir, key + ".nrrd"), arr[pos], spacing_xyz, origin_xyz,
+                                      compress, level)
+        return {k: j.result() for k, j in jobs.items()}

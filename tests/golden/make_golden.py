@@ -260,7 +260,60 @@ def shape_goldens():
     np.savez_compressed(os.path.join(HERE, "shape_random.npz"), **out)
 
 
+def shape2d_goldens():
+    """2-D shape coefficients of the compiled reference _cshape (calculate_coefficients2D, cshape.c:420-595) on padded
+    random / structured single-slice masks -> shape2d_golden.npz"""
+    import build_ref
+    cs = build_ref.load("_cshape")
+    rng = np.random.default_rng(7)
+    yy, xx = np.mgrid[0:40, 0:48]
+    masks = {
+        "disc": ((yy - 20) ** 2 / 1.0 + (xx - 22) ** 2 / 1.7) < 150,
+        "noise": rng.random((30, 33)) < 0.5,
+        "sparse": rng.random((25, 25)) < 0.08,
+        "touching_border": np.zeros((12, 14), bool),
+        "single": np.zeros((5, 5), bool),
+        "checker": (yy[:10, :11] + xx[:10, :11]) % 2 == 0,
+        "ring": (((yy - 20) ** 2 + (xx - 24) ** 2) < 300) & (((yy - 20) ** 2 + (xx - 24) ** 2) > 90),
+    }
+    masks["touching_border"][0:5, 9:14] = True
+    masks["single"][2, 2] = True
+    out = {}
+    for name, m in masks.items():
+        sp = np.array([1.0 + 0.37 * (len(name) % 3), 0.8 + 0.11 * (len(name) % 4)])
+        ref = cs.calculate_coefficients2D(np.pad(m.astype(np.int8), 1), sp)
+        out[name + "_mask"], out[name + "_spacing"], out[name + "_coeff"] = m, sp, np.array(ref)
+        print("shape2D coeff", name, ref)
+    np.savez_compressed(os.path.join(HERE, "shape2d_golden.npz"), **out)
+
+
+def resample_goldens():
+    """the reference's bundled breast1 case (small enough to commit whole) + every `original_*` value of the
+    `breast1_resampling` column of data/baseline/baseline_<class>.csv (resampledPixelSpacing [2,2,2], sitkBSpline):
+    the pin of the resampling step -> resample_breast1.npz"""
+    import csv
+    import ref_harness as rh
+    img, sp = rh.read_nrrd(os.path.join(rh.REF_ROOT, "data", "breast1_image.nrrd"))
+    msk, _ = rh.read_nrrd(os.path.join(rh.REF_ROOT, "data", "breast1_label.nrrd"))
+    exp = {}
+    for cls in ("firstorder", "glcm", "glrlm", "glszm", "gldm", "ngtdm", "shape"):
+        rows = list(csv.reader(open(os.path.join(rh.REF_ROOT, "data", "baseline", f"baseline_{cls}.csv"))))
+        i = rows[0].index("breast1_resampling")
+        for r in rows[1:]:
+            if r[0].startswith("original_"):
+                exp[r[0]] = float(r[i])
+    np.savez_compressed(os.path.join(HERE, "resample_breast1.npz"), image=img, mask=msk.astype(np.uint8), spacing=np.array(sp),
+                        names=np.array(sorted(exp)), values=np.array([exp[k] for k in sorted(exp)]))
+    print("resample golden", img.shape, sp, len(exp), "values")
+
+
 if __name__ == "__main__":
+    if "--resample-only" in sys.argv:
+        resample_goldens()
+        sys.exit(0)
+    if "--shape2d-only" in sys.argv:
+        shape2d_goldens()
+        sys.exit(0)
     if "--shape-only" in sys.argv:
         shape_goldens()
         sys.exit(0)

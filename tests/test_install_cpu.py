@@ -36,17 +36,18 @@ def test_install_registers_classes_and_rebinds_cmatrices(rad):
         assert rad.getFeatureClasses()[name] is cls
         # the reference accepts a class by the NAME of a base in its MRO (radiomics/__init__.py:95-99)
         assert "RadiomicsFeaturesBase" in [k.__name__ for k in cls.__mro__]
-    assert "shape2D" in rad.getFeatureClasses()                       # untouched reference class
     assert rad.cMatrices is cmatrices
     for mod in ("glcm", "glrlm", "glszm", "gldm", "ngtdm", "firstorder"):
         assert importlib.import_module(f"{rad.__name__}.{mod}").cMatrices is cmatrices
-    # cShape: the 3-D entry point is ours, the 2-D one still resolves (to the reference's compiled _cshape)
+    # cShape: both entry points of the reference's _cshape are served (radiomics/src/_cshape.c:33-39), and a name the
+    # replacement does not know still resolves to the reference's own extension
     assert rad.cShape is cshape
     assert rad.cShape.calculate_coefficients is cshape.calculate_coefficients
-    assert rad.cShape.calculate_coefficients2D is orig_cshape.calculate_coefficients2D
+    assert rad.cShape.calculate_coefficients2D is cshape.calculate_coefficients2D
     sh2 = importlib.import_module(f"{rad.__name__}.shape2D")
     importlib.reload(sh2)                                              # a later (re)import of shape2D keeps working
-    assert sh2.cShape.calculate_coefficients2D is orig_cshape.calculate_coefficients2D
+    assert sh2.cShape.calculate_coefficients2D is cshape.calculate_coefficients2D
+    assert cshape.__doc__ and cshape._fallback is orig_cshape
     with pytest.raises(AttributeError):
         cshape.no_such_function
 
@@ -54,10 +55,10 @@ def test_install_registers_classes_and_rebinds_cmatrices(rad):
 def test_feature_names_and_docstrings_match_the_reference_classes(rad):
     """reference tests/test_docstrings.py: every get<Name>FeatureValue has a docstring; names equal the reference's"""
     from pyradiomics_b200 import featureclasses as FC
-    for name in ("glcm", "glrlm", "glszm", "gldm", "ngtdm", "firstorder"):
+    for name in ("glcm", "glrlm", "glszm", "gldm", "ngtdm", "firstorder", "shape", "shape2D"):
         ref_cls = getattr(importlib.import_module(f"{rad.__name__}.{name}"), {"glcm": "RadiomicsGLCM", "glrlm": "RadiomicsGLRLM",
                           "glszm": "RadiomicsGLSZM", "gldm": "RadiomicsGLDM", "ngtdm": "RadiomicsNGTDM",
-                          "firstorder": "RadiomicsFirstOrder"}[name])
+                          "firstorder": "RadiomicsFirstOrder", "shape": "RadiomicsShape", "shape2D": "RadiomicsShape2D"}[name])
         ours = {**FC.FEATURE_CLASSES, **FC.NEXT_CLASSES}[name]
         assert ours.getFeatureNames() == ref_cls.getFeatureNames()
         for f in ours.getFeatureNames():

@@ -74,3 +74,18 @@ def test_committed_table_is_what_the_generator_derives():
     for cfg, tris in enumerate(table):
         flat = [e for t in tris for e in t]
         assert list(tri[cfg][:len(flat)]) == flat and (tri[cfg][len(flat):] == -1).all(), cfg
+
+
+SHAPE2D = ["disc", "noise", "sparse", "touching_border", "single", "checker", "ring"]
+
+
+@pytest.mark.parametrize("name", SHAPE2D)
+def test_shape2d_restatement_matches_compiled_reference_goldens(name):
+    """oracle/shape_np.coefficients2d against the reference's calculate_coefficients2D (tests/golden/shape2d_golden.npz,
+    written by make_golden.py --shape2d-only from the compiled _cshape)"""
+    import shape_np as S
+    d = np.load(os.path.join(G, "shape2d_golden.npz"))
+    per, sur, dia = S.coefficients2d(np.pad(d[name + "_mask"], 1), d[name + "_spacing"])
+    ref = d[name + "_coeff"]
+    assert per == pytest.approx(ref[0], rel=1e-13) and sur == pytest.approx(ref[1], rel=1e-12, abs=1e-14)
+    assert dia == ref[2]

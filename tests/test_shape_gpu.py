@@ -87,3 +87,43 @@ def test_large_roi_against_compiled_reference():
     assert sa == pytest.approx(ref[0], rel=1e-11)
     assert vol == pytest.approx(ref[1], rel=1e-11)
     assert tuple(dia) == tuple(ref[2])
+
+
+SHAPE2D = ["disc", "noise", "sparse", "touching_border", "single", "checker", "ring"]
+
+
+@pytest.mark.parametrize("name", SHAPE2D)
+def test_calculate_coefficients2d_matches_reference(name):
+    """CUDA marching squares + all-pairs diameter (rb_calculate_coefficients2D) against the compiled reference's outputs"""
+    from pyradiomics_b200 import cshape
+    d = np.load(os.path.join(G, "shape2d_golden.npz"))
+    per, sur, dia = cshape.calculate_coefficients2D(np.pad(d[name + "_mask"], 1), d[name + "_spacing"])
+    ref = d[name + "_coeff"]
+    assert per == pytest.approx(ref[0], rel=1e-12)
+    assert sur == pytest.approx(ref[1], rel=1e-12, abs=1e-13)
+    assert dia == ref[2]                                    # bit-identical: same double operations, max is order-free
+
+
+def test_shape2d_class_matches_oracle_features_and_guards():
+    sys.path.insert(0, os.path.join(HERE, "..", "oracle"))
+    import shape_np as S
+    from pyradiomics_b200 import featureclasses as FC, image as I
+    d = np.load(os.path.join(G, "shape2d_golden.npz"))
+    for name in ("disc", "ring", "noise"):
+        m, sp = d[name + "_mask"], d[name + "_spacing"]
+        ref = S.features2d(m, sp)
+        img2 = I.ArrayImage(np.zeros(m.shape, np.int16), sp[::-1])
+        got = FC.RadiomicsShape2D(img2, I.ArrayImage(m.astype(np.uint8), sp[::-1])).execute()
+        assert set(got) == set(FC.RadiomicsShape2D.NAMES)
+        for k, v in got.items():
+            assert float(v) == pytest.approx(ref[k], rel=1e-10), (name, k)
+        # the same slice as a 3-D image with force2D
+        m3 = m[None]
+        img3 = I.ArrayImage(np.zeros(m3.shape, np.int16), (sp[1], sp[0], 3.0))
+        got3 = FC.RadiomicsShape2D(img3, I.ArrayImage(m3.astype(np.uint8), (sp[1], sp[0], 3.0)), force2D=True, force2Ddimension=0).execute()
+        for k, v in got3.items():
+            assert float(v) == pytest.approx(ref[k], rel=1e-10), (name, k)
+    with pytest.raises(ValueError):
+        FC.RadiomicsShape2D(img3, I.ArrayImage(m3.astype(np.uint8)), force2D=False).execute()
+    with pytest.raises(NotImplementedError):
+        FC.RadiomicsShape2D(img2, I.ArrayImage(m.astype(np.uint8)), voxelBased=True)
