@@ -28,7 +28,13 @@
 namespace rb {
 
 constexpr uint32_t LZ_LOW = 0x36DB6DBu;       // window positions p (a*9 + b*3 + c) with c < 2: lower ends of the pairs (p, p+1)
-constexpr int LZ_ACC = 3;                     // interleaved partial sums per reduction
+#ifndef LZ_ACC_N
+#define LZ_ACC_N 3
+#endif
+#ifndef LZ_EIG_EXACT_STATIC
+#define LZ_EIG_EXACT_STATIC 0      // 1: a task whose node count fills its template takes the fully static eigenvalue search
+#endif
+constexpr int LZ_ACC = LZ_ACC_N;               // interleaved partial sums per reduction
 constexpr int LZ_NARR = 5;                    // per-thread shared arrays: U, S, IR, D, E (N doubles each)
 
 RB_HD constexpr int lz_smem_doubles(int N) { return LZ_NARR * N; }
@@ -257,6 +263,10 @@ RB_HD double glcm_lanczos_axis(const int* wl, const TT& T, double* sm, int st, i
 #pragma unroll
   for (int i = 0; i < N - 1; i++) { d[i] = D[(size_t)i * st]; e[i] = E[(size_t)i * st]; }
   double hi, lo;
+#if LZ_EIG_EXACT_STATIC
+  if (n == N) tridiag_extreme_pair_static<N - 1, false>(d, e, &hi, &lo, live);
+  else
+#endif
   tridiag_extreme_pair_dyn<N - 1>(d, e, n - 1, &hi, &lo, live && n >= 2);      // the deflated space has n - 1 dimensions
   return fmax(fabs(hi), fabs(lo));
 }

@@ -2,7 +2,7 @@
 // radiomics/src/cmatrices.c: calculate_glcm :4-92, calculate_gldm :660-754, calculate_ngtdm :543-658, calculate_glrlm
 // :299-541, calculate_glszm :94-279).  Round-2 rebuild of the segment path on the north-star design:
 //
-//   seg_tile_kernel   GLCM + GLDM + NGTDM in ONE pass: a CTA stages a (TZ+2H) x (TY+2H) x (TX+2H) box of the level
+//   seg_tile_kernel   GLCM + GLDM + NGTDM in ONE pass: a CTA stages a (TZ+2H) x (TY+2H) x 96-byte box of the level
 //                     volume in shared memory -- by TMA (cp.async.bulk.tensor.3d, out-of-volume coordinates are
 //                     zero-filled by the hardware = "unmasked", double-buffered on an mbarrier) when the row pitch
 //                     allows a tensor map, else by cooperative loads -- walks the 13 / 26 offsets in shared memory
@@ -34,6 +34,10 @@ struct SegVol {
 };
 
 constexpr int ST_TX = 64, ST_THREADS = 256;
+// The staged box starts ST_XOFF columns left of the tile: TMA wants the innermost start coordinate 16-byte aligned (a box
+// at x0-1 faults with "illegal instruction", at x0-16 it loads and zero-fills: scripts/probes/tma_probe.cu,
+// profiles/r02_tma_probe.txt), and tiles start at multiples of 64.
+constexpr int ST_XOFF = 16, ST_BX = ST_XOFF + ST_TX + 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -57,7 +61,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 struct SegTileGeom {
   int tz, ty;            // tile = tz x ty x ST_TX voxels (tz * ty * ST_TX = 8 * ST_THREADS)
   int H;                 // halo = largest offset component
-  int bx, by, bz;        // staged box: bx = (ST_TX + 2H rounded up to 16) bytes per row, by = ty + 2H rows, bz = tz + 2H planes
+  int bx, by, bz;        // staged box: bx = ST_BX bytes per row (16-byte aligned start), by = ty + 2H rows, bz = tz + 2H planes
   int ntx, nty, ntz;     // tiles per axis
   int glcm_shared;       // GLCM histogram lives in shared memory
 };
@@ -98,12 +102,12 @@ seg_tile_kernel(const uint8_t* __restrict__ lev, SegVol V, const __grid_constant
     if (TMA) {
       if (tid == 0) {
         mbar_expect_tx(&bar[buf], (uint32_t)box);
-        tma_load_3d(dst, &tmap, &bar[buf], x0 - H, y0 - H, z0 - H);
+        tma_load_3d(dst, &tmap, &bar[buf], x0 - ST_XOFF, y0 - H, z0 - H);
       }
     } else {
       for (int i = tid; i < box; i += ST_THREADS) {
         const int c = i % G.bx, r = i / G.bx % G.by, p = i / (G.bx * G.by);
-        const int x = x0 - H + c, y = y0 - H + r, z = z0 - H + p;
+        const int x = x0 - ST_XOFF + c, y = y0 - H + r, z = z0 - H + p;
         dst[i] = (x >= 0 && x < V.X && y >= 0 && y < V.Y && z >= 0 && z < V.Z) ? lev[(long long)z * V.pitch_z + (long long)y * V.pitch_y + x]
                                                                                : (uint8_t)0;
       }
@@ -128,7 +132,7 @@ seg_tile_kernel(const uint8_t* __restrict__ lev, SegVol V, const __grid_constant
       const int v = k * ST_THREADS + tid;           // voxel of the tile: x fastest
       const int lx = v % ST_TX, ly = v / ST_TX % G.ty, lz = v / (ST_TX * G.ty);
       if (x0 + lx >= V.X || y0 + ly >= V.Y || z0 + lz >= V.Z) continue;
-      const int c = ((lz + H) * G.by + (ly + H)) * G.bx + (lx + H);
+      const int c = ((lz + H) * G.by + (ly + H)) * G.bx + (lx + ST_XOFF);
       const int gi = tl[c];
       if (!gi) continue;
       int dep = 0, cnt = 0, sum = 0;
@@ -257,11 +261,10 @@ static int sm_count() {
   return sms;
 }
 
-// B200_SEG_TMA=1 selects the TMA staging, 0 / unset the cooperative loads (see DESIGN.md section 3.2 for why the
-// default is the cooperative path on this pool's boxes)
+// B200_SEG_TMA=0 forces the cooperative-load staging (A/B runs, tests); default: TMA whenever a tensor map can be built
 static bool seg_tma_enabled() {
   const char* e = getenv("B200_SEG_TMA");
-  return e && e[0] == '1';
+  return !(e && e[0] == '0');
 }
 
 // GLCM (flag 1) / GLDM (2) / NGTDM (4) of one packed uint8 level volume in one pass; outputs are HOST float64 buffers in
@@ -292,7 +295,7 @@ int segment_tile_matrices(const uint8_t* lev, int nd, int Z, int Y, int X, const
   SegTileGeom G;
   G.H = H;
   if (Z == 1) { G.tz = 1; G.ty = 32; } else { G.tz = 4; G.ty = 8; }
-  G.bx = (ST_TX + 2 * H + 15) & ~15; G.by = G.ty + 2 * H; G.bz = G.tz + 2 * H;
+  G.bx = ST_BX; G.by = G.ty + 2 * H; G.bz = G.tz + 2 * H;
   G.ntx = (X + ST_TX - 1) / ST_TX; G.nty = (Y + G.ty - 1) / G.ty; G.ntz = (Z + G.tz - 1) / G.tz;
   const int box_al = (G.bx * G.by * G.bz + 127) & ~127;
   const size_t n_gl = (size_t)Ng * Ng * na, n_gd = (size_t)Ng * (2 * (2 * na) + 1), n_ng = (size_t)Ng * (2 * na + 2);

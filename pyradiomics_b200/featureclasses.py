@@ -86,14 +86,29 @@ def getProgressReporter(*args, **kwargs):
 
 
 # ---- per-image device state shared by the feature classes -----------------------
+_FP_POOL = None
+
+
 def _fingerprint(a):
-    """cheap content key of a host array (shape, dtype, wrapped 64-bit sum, tail bytes): the same image handed to
-    the five classes one after the other (featureextractor.py:586-602) hits the cache; an edited image does not"""
+    """content key of a host array (shape, dtype, wrapped 64-bit sums over the WHOLE buffer, tail bytes): the same image
+    handed to the five classes one after the other (featureextractor.py:586-602) hits the cache; an edited image does
+    not.  Large arrays are summed by a few threads (NumPy releases the GIL): a 512^3 int16 image costs a few ms."""
+    global _FP_POOL
     a = np.ascontiguousarray(a)
     b = a.reshape(-1).view(np.uint8)
     n8 = b.size // 8 * 8
-    s = int(b[:n8].view(np.uint64).sum(dtype=np.uint64)) if n8 else 0
-    s2 = int(b[:n8].view(np.uint64)[::4099].sum(dtype=np.uint64)) if n8 else 0
+    w = b[:n8].view(np.uint64)
+    if w.size > (1 << 22):
+        import concurrent.futures as cf
+        if _FP_POOL is None:
+            _FP_POOL = cf.ThreadPoolExecutor(max_workers=8)
+        parts = np.array_split(w, 16)
+        sums = list(_FP_POOL.map(lambda p: (int(p.sum(dtype=np.uint64)), int(p[::61].sum(dtype=np.uint64))), parts))
+        s = sum(x[0] for x in sums) & 0xFFFFFFFFFFFFFFFF
+        s2 = sum((k + 1) * x[1] for k, x in enumerate(sums)) & 0xFFFFFFFFFFFFFFFF
+    else:
+        s = int(w.sum(dtype=np.uint64)) if n8 else 0
+        s2 = int(w[::61].sum(dtype=np.uint64)) if n8 else 0
     return (a.shape, a.dtype.str, s, s2, bytes(b[n8:]))
 
 
@@ -101,9 +116,11 @@ class DeviceImage:
     """One (image, ROI mask, binning) discretised ONCE on the GPU: rb_minmax_dev -> rb_digitize_dev ->
     rb_pack_levels_dev (reference: binImage in every class constructor, base.py:119-125, i.e. 5x per image)."""
 
-    def __init__(self, imageArray, maskArray, settings):
+    def __init__(self, imageArray, maskRaw, label, masked, settings):
         img_t = imageoperations._to_device(imageArray)
-        msk_t = imageoperations._to_device(maskArray)
+        # the ROI mask is formed on the device: label compare of the raw mask (or all ones for an unmasked kernel)
+        raw_t = imageoperations._to_device(maskRaw)
+        msk_t = (raw_t == label).to(torch.uint8) if masked else torch.ones(raw_t.shape, dtype=torch.uint8, device=raw_t.device)
         lev_t, self.edges = imageoperations.bin_image_device(img_t, msk_t, **settings)
         Ng = int(lev_t.max().item())
         self.levels, presence = voxel.pack_levels(lev_t, msk_t, max(Ng, 1))
@@ -144,12 +161,12 @@ _DEVICE_IMAGES = collections.OrderedDict()
 _DEVICE_IMAGES_MAX = 2
 
 
-def device_image(imageArray, maskArray, settings):
-    key = (_fingerprint(imageArray), _fingerprint(maskArray), repr(settings.get("binWidth", 25)), repr(settings.get("binCount")),
-           torch.cuda.current_device())
+def device_image(imageArray, maskRaw, label, masked, settings):
+    key = (_fingerprint(imageArray), _fingerprint(maskRaw), label, bool(masked), repr(settings.get("binWidth", 25)),
+           repr(settings.get("binCount")), torch.cuda.current_device())
     st = _DEVICE_IMAGES.get(key)
     if st is None:
-        st = DeviceImage(imageArray, maskArray, settings)
+        st = DeviceImage(imageArray, maskRaw, label, masked, settings)
         _DEVICE_IMAGES[key] = st
         while len(_DEVICE_IMAGES) > _DEVICE_IMAGES_MAX:
             _DEVICE_IMAGES.popitem(last=False)
@@ -188,22 +205,37 @@ class RadiomicsFeaturesBase:
         self._rawImageArray = I.as_array(inputImage)
         self._imageArray = None
         self._device = None
-        labelMask = I.as_array(inputMask) == self.label
-        if self.voxelBased:
-            self.masked = kwargs.get("maskedKernel", True)
-            self._labelledVoxelCoordinates = None      # lazy: 3 x Nvox int64 (3.2 GB and seconds of np.where at 512^3)
-            self._centerMask = labelMask
-            self.maskArray = labelMask if self.masked else np.ones(self._rawImageArray.shape, dtype=bool)
-        else:
-            self.maskArray = labelMask
+        self._maskRaw = I.as_array(inputMask)
+        self._labelMask = None                         # lazy: the label compare of a 512^3 mask is 0.1 s of host time per class
+        self._maskArray = None
+        self.masked = kwargs.get("maskedKernel", True) if self.voxelBased else True
+        self._labelledVoxelCoordinates = None          # lazy: 3 x Nvox int64 (3.2 GB and seconds of np.where at 512^3)
         setattr(self, self.MATRIX_ATTR, None)
         self._initBinning()
 
     # ---- discretisation on the GPU, shared by the classes that see the same image (reference base.py:119-125)
     def _initBinning(self):
-        self._device = device_image(self._rawImageArray, self.maskArray, self.settings)
+        self._device = device_image(self._rawImageArray, self._maskRaw, self.label, self.masked, self.settings)
         self.coefficients["grayLevels"] = self._device.grayLevels
         self.coefficients["Ng"] = self._device.Ng
+
+    @property
+    def _centerMask(self):
+        """boolean ROI mask (the voxels that get a value in voxel-based mode)"""
+        if self._labelMask is None:
+            self._labelMask = self._maskRaw == self.label
+        return self._labelMask
+
+    @property
+    def maskArray(self):
+        """the reference's ``self.maskArray``: the ROI, or everything for an unmasked voxel kernel (base.py:100-104)"""
+        if self._maskArray is None:
+            self._maskArray = self._centerMask if self.masked else np.ones(self._rawImageArray.shape, dtype=bool)
+        return self._maskArray
+
+    @maskArray.setter
+    def maskArray(self, value):
+        self._maskArray = value
 
     @property
     def labelledVoxelCoordinates(self):

@@ -14,6 +14,7 @@ from pyradiomics_b200 import _lib, cmatrices, cshape, featureclasses as FC, imag
 
 args = [a for a in sys.argv[1:]]
 N = int(args.pop(0)) if args and args[0].isdigit() else 20
+N16 = N - N % 16 if N >= 16 else N
 fams = args or ["fast", "generic", "matrix", "filters", "shape", "firstorder"]
 rng = np.random.default_rng(0)
 
@@ -64,6 +65,19 @@ if "matrix" in fams:
         cmatrices.calculate_gldm(lev, m, [1], 32, 0, False, -1, 1, vox)
         cmatrices.calculate_ngtdm(lev, m, [1], 32, False, -1, 1, vox)
         print("matrix ok", float(P.sum()), flush=True)
+    # a row pitch that is a multiple of 16 bytes: the fused tile kernel stages its boxes by TMA (else cooperative loads)
+    lt, mt = np.ascontiguousarray(lev[:, :, :N16]), np.ascontiguousarray(mask_rag[:, :, :N16])
+    for tma in ("1", "0"):
+        os.environ["B200_SEG_TMA"] = tma
+        cmatrices.calculate_glcm(lt, mt, [1, 2], 32, False, -1)
+        cmatrices.calculate_gldm(lt, mt, [1], 32, 1, False, -1)
+        cmatrices.calculate_ngtdm(lt, mt, [1], 32, False, -1)
+        levd, _ = voxel.pack_levels(torch.as_tensor(lt).cuda(), torch.as_tensor(mt).cuda(), 32)
+        cmatrices.segment_texture_device(levd, [1], 32, 0, False, -1)
+        cmatrices.calculate_glrlm_device(levd, 32, max(lt.shape), False, -1)
+        cmatrices.calculate_glszm_device(levd, 32, False, -1)
+    del os.environ["B200_SEG_TMA"]
+    print("matrix tma/coop ok", flush=True)
     cmatrices.calculate_glcm(lev[3], mask_rag[3], [1, 2], 32, False, -1)          # 2-D
     cmatrices.calculate_glszm(lev[3], mask_rag[3], 32, int(mask_rag[3].sum()), False, -1)
 
@@ -77,12 +91,15 @@ if "filters" in fams:
         names = [n for _, n, _ in IO.getWaveletImage(im, None)]
         names += [n for _, n, _ in IO.getLoGImage(im, None, sigma=[1.0, 2.0])]
     torch.cuda.synchronize()
-    print("filters ok", len(names), flush=True)
+    ri, rm = IO.resampleImage(raw.astype(np.int16), mask_rag.astype(np.uint8), resampledPixelSpacing=[1.6, 1.6, 1.6], padDistance=2)
+    torch.cuda.synchronize()
+    print("filters ok", len(names), "resampled", ri.array.shape, flush=True)
 
 if "shape" in fams:
     zz, yy, xx = np.indices(mask_full.shape)
     ball = ((zz - N / 2) ** 2 + (yy - N / 2) ** 2 + (xx - N / 2) ** 2) < (N / 2.5) ** 2
     print("shape", cshape.calculate_coefficients(np.pad(ball & mask_rag, 1), (1.0, 0.8, 0.7)), flush=True)
+    print("shape2D", cshape.calculate_coefficients2D(np.pad((ball & mask_rag)[N // 2], 1), (0.8, 0.7)), flush=True)
 
 if "firstorder" in fams:
     raw = (vols["smooth"].astype(np.float64) - 1) * 25 + rng.random(mask_full.shape) * 20

@@ -157,7 +157,7 @@ def test_segment_kernels_tma_equals_cooperative_equals_legacy(shape, dist, monke
     lev = rng.integers(1, 25, shape).astype(np.int32)
     msk = rng.random(shape) < 0.8
     res = {}
-    modes = ("tma", "coop", "legacy") if os.environ.get("B200_TEST_TMA") == "1" else ("coop", "legacy")
+    modes = ("tma", "coop", "legacy")
     for mode in modes:
         monkeypatch.setenv("B200_SEG_TMA", "0" if mode == "coop" else "1")
         monkeypatch.setenv("B200_SEG_LEGACY", "1" if mode == "legacy" else "0")

@@ -72,4 +72,6 @@ def test_resample_variants_against_oracle(case):
         assert np.allclose(ri.array, oi, rtol=1e-5, atol=1e-3)
     else:
         d = np.abs(ri.array.astype(np.int64) - oi.astype(np.int64))
-        assert d.max() <= 1 and (d > 0).mean() < 1e-3          # truncation of values that differ by 1e-8: at most a rare off-by-one
+        # truncation of values that differ by 1e-12: at most an off-by-one, rare for the B-spline; linear interpolation of
+        # integers lands exactly ON integers wherever the grids coincide, so there the last bit decides more often
+        assert d.max() <= 1 and (d > 0).mean() < (0.03 if case == "linear" else 1e-3)
