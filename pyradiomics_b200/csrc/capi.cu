@@ -30,6 +30,7 @@ int glcm_alive_angles(const void* lev, int level_bytes, const uint8_t* centers, 
 int pack_levels(const int32_t* image, const uint8_t* mask, long long n, int Ng, void* lev, uint32_t* presence,
                 int* status, cudaStream_t st);
 bool glcm_fast_applicable(int cls, int level_bytes, const VoxParams& P);
+int glcm_release_queues();
 int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P, double* out, long long fstride,
                      int z0, int z1, int out_z0, cudaStream_t st);
 
@@ -136,6 +137,8 @@ int rb_device_count(void) {
   if (e != cudaSuccess) return fail(RB_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
   return n;
 }
+
+int rb_release_device_caches(void) { return glcm_release_queues(); }
 
 int rb_num_features(int cls) { return (cls < 0 || cls > 4) ? RB_ERR_ARG : kNumFeatures[cls]; }
 

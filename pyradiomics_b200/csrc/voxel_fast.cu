@@ -51,9 +51,25 @@ bool glcm_fast_applicable(int cls, int level_bytes, const VoxParams& P) {
 
 // per (device, stream) task queue, grown on demand
 struct GlcmQueue { GlcmTask* q = nullptr; double* res = nullptr; unsigned* count = nullptr; size_t cap = 0; };
+static std::mutex g_queue_mu;
+static std::map<std::pair<int, cudaStream_t>, GlcmQueue> g_queue_cache;
+// rb_release_device_caches: give the eigen-task queues of the current device back (up to 1.15 GB per stream that ran GLCM)
+int glcm_release_queues() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return RB_ERR_CUDA;
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(g_queue_mu);
+  for (auto it = g_queue_cache.begin(); it != g_queue_cache.end();) {
+    if (it->first.first == dev) {
+      cudaFree(it->second.q); cudaFree(it->second.res); cudaFree(it->second.count);
+      it = g_queue_cache.erase(it);
+    } else ++it;
+  }
+  return RB_OK;
+}
 static GlcmQueue* glcm_queue(cudaStream_t st, size_t need) {
-  static std::mutex mu;
-  static std::map<std::pair<int, cudaStream_t>, GlcmQueue> cache;
+  std::mutex& mu = g_queue_mu;
+  auto& cache = g_queue_cache;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
   std::lock_guard<std::mutex> lk(mu);

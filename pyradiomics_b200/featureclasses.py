@@ -162,8 +162,13 @@ _DEVICE_IMAGES_MAX = 2
 
 
 def device_image(imageArray, maskRaw, label, masked, settings):
-    key = (_fingerprint(imageArray), _fingerprint(maskRaw), label, bool(masked), repr(settings.get("binWidth", 25)),
-           repr(settings.get("binCount")), torch.cuda.current_device())
+    """the device-resident discretised image of (image, mask, label, binning): built on first sight, shared afterwards.
+    The cache key is the CONTENT of image and mask (_fingerprint: ~25 ms for a 512^3 case) unless the caller passes
+    ``b200_image_key=<hashable>`` -- its promise that image and mask are the ones it used with that key before (a
+    pyradiomics extraction already has such a key: the sha1 of the image in its diagnostics, generalinfo.py)."""
+    ident = settings.get("b200_image_key")
+    content = ("key", ident, imageArray.shape, maskRaw.shape) if ident is not None else (_fingerprint(imageArray), _fingerprint(maskRaw))
+    key = (content, label, bool(masked), repr(settings.get("binWidth", 25)), repr(settings.get("binCount")), torch.cuda.current_device())
     st = _DEVICE_IMAGES.get(key)
     if st is None:
         st = DeviceImage(imageArray, maskRaw, label, masked, settings)
@@ -175,9 +180,11 @@ def device_image(imageArray, maskRaw, label, masked, settings):
     return st
 
 
-def clear_device_cache():
-    """drop the cached device-resident discretised images"""
+def clear_device_cache(release_queues=False):
+    """drop the cached device-resident discretised images (and, on request, the library's GLCM eigen-task queues)"""
     _DEVICE_IMAGES.clear()
+    if release_queues:
+        _lib.check(_lib.lib().rb_release_device_caches(), "release_device_caches")
 
 
 class RadiomicsFeaturesBase:
