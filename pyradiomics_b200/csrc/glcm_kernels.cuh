@@ -44,7 +44,7 @@ struct GlcmTask {
 #define GF_SOLVE_MINB_L 2
 #endif
 #ifndef GF_SOLVE_TILE
-#define GF_SOLVE_TILE 2048
+#define GF_SOLVE_TILE 4096
 #endif
 constexpr int GF_LZ_SMEM_BYTES = LZ_NARR * 18 * 128 * (int)sizeof(double);
 constexpr int glcm_phaseA_smem_bytes(int nt) { return 27 * nt * (int)(sizeof(uint32_t) + sizeof(uint8_t)); }

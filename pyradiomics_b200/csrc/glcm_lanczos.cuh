@@ -34,6 +34,9 @@ constexpr uint32_t LZ_LOW = 0x36DB6DBu;       // window positions p (a*9 + b*3 +
 #ifndef LZ_EIG_EXACT_STATIC
 #define LZ_EIG_EXACT_STATIC 0      // 1: a task whose node count fills its template takes the fully static eigenvalue search
 #endif
+#ifndef LZ_SEGSUM
+#define LZ_SEGSUM 1                // 1: neighbour sums by a segmented scan over node-sorted endpoint lists (no smem read-modify-write chain)
+#endif
 constexpr int LZ_ACC = LZ_ACC_N;               // interleaved partial sums per reduction
 constexpr int LZ_NARR = 5;                    // per-thread shared arrays: U, S, IR, D, E (N doubles each)
 
@@ -169,6 +172,49 @@ RB_HD double glcm_lanczos_axis(const int* wl, const TT& T, double* sm, int st, i
     ida[t / 6] |= a << (5 * (t % 6));
     idb[t / 6] |= b << (5 * (t % 6));
   }
+#if LZ_SEGSUM
+  // ---- endpoint lists sorted by owner node (counting sort through shared memory, once per task): entry e of node i's
+  // run [off_i, off_i + R_i) holds the node at the other end of one of i's pairs, in pair order.  The Lanczos loop then
+  // gathers U[adj_e] with 36 INDEPENDENT loads and sums each run in registers; the former S[a] += U[b] form was a chain
+  // of 36 shared-memory read-modify-writes per step that the compiler must keep in order (a and b may alias): ~1.4k
+  // cycles of exposed latency per step with two warps per scheduler.  Same terms in the same order: bit-identical sums.
+  uint32_t adjw[6];                                        // 6 entries of 5 bits per word
+  uint64_t firstm = 0, lastm = 0;                          // bit e: entry e opens / closes a run
+  const int cnt = 2 * RB_POPC(VL);
+  {
+    int off = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const int Ri = (int)Rd[i];
+      *reinterpret_cast<int*>(&S[(size_t)i * st]) = off;   // cursor of node i
+      if (Ri) { firstm |= 1ull << off; lastm |= 1ull << (off + Ri - 1); }
+      off += Ri;
+    }
+    int* const ADJ = reinterpret_cast<int*>(D);            // D and E are contiguous: 4N >= 36 ints per thread, int e at
+#define LZ_ADJ(e) ADJ[(size_t)((e) >> 1) * st * 2 + ((e) & 1)]   /* double slot e/2, half e%2 */
+#pragma unroll
+    for (int t = 0; t < 18; t++) {
+      const int p = (t / 2) * 3 + (t % 2);
+      if (VL >> p & 1u) {
+        const int a = (ida[t / 6] >> (5 * (t % 6))) & 31u, b = (idb[t / 6] >> (5 * (t % 6))) & 31u;
+        int* const ca = reinterpret_cast<int*>(&S[(size_t)a * st]);
+        const int sa = *ca; *ca = sa + 1; LZ_ADJ(sa) = b;
+        int* const cb = reinterpret_cast<int*>(&S[(size_t)b * st]);
+        const int sb = *cb; *cb = sb + 1; LZ_ADJ(sb) = a;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) adjw[k] = 0;
+#pragma unroll
+    for (int e = 0; e < 36; e++) {
+      const int v = e < cnt ? LZ_ADJ(e) : 0;
+      adjw[e / 6] |= (uint32_t)v << (5 * (e % 6));
+    }
+#undef LZ_ADJ
+#pragma unroll
+    for (int i = 0; i < N; i++) S[(size_t)i * st] = 0.0;   // nodes >= n own no run: their sum stays 0
+  }
+#endif
   // ---- start vector (generic fixed components), D-orthogonal to the constant vector, D-normalised
   double y0[N], y1[N];
   double Ssum = 0, dot = 0;
@@ -195,6 +241,22 @@ RB_HD double glcm_lanczos_axis(const int* wl, const TT& T, double* sm, int st, i
   E[0] = 0;
   // ---- N-1 Lanczos steps (the deflated space has n-1 <= N-1 dimensions; see the file header for breakdowns)
   for (int j = 0; j < N - 1; j++) {
+#if LZ_SEGSUM
+#pragma unroll
+    for (int i = 0; i < N; i++) U[(size_t)i * st] = y1[i];
+    {
+      double acc = 0.0;
+      int r = -1;                                          // run index = owner node (every node < n owns one run)
+#pragma unroll
+      for (int e = 0; e < 36; e++) {
+        const double g = U[(size_t)((adjw[e / 6] >> (5 * (e % 6))) & 31u) * st];
+        const bool fst = firstm >> e & 1ull;
+        r += fst;
+        acc = fma(acc, fst ? 0.0 : 1.0, g);                // acc + g inside a run, g at its first entry (exact either way)
+        if (lastm >> e & 1ull) S[(size_t)r * st] = acc;
+      }
+    }
+#else
 #pragma unroll
     for (int i = 0; i < N; i++) { U[(size_t)i * st] = y1[i]; S[(size_t)i * st] = 0.0; }
     // neighbour sums: S[a] += y[b], S[b] += y[a] for every valid pair (a self pair adds 2 y[a])
@@ -208,6 +270,7 @@ RB_HD double glcm_lanczos_axis(const int* wl, const TT& T, double* sm, int st, i
         S[b] += ua;
       }
     }
+#endif
     // z = W y1 - beta y0 (kept in y0's registers); alpha = <y1, W y1>_D = sum y1_i s_i.  Every reduction below runs
     // on LZ_ACC interleaved partial sums: with two warps per scheduler a single 18-long DFMA chain is exposed latency.
     double al[LZ_ACC];

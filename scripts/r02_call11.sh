@@ -41,3 +41,5 @@ for ax in (2, 1, 0):
 torch.cuda.synchronize()
 PY
 ls -la $O
+for f in $O/*.ncu-rep; do ncu -i $f --page raw --csv --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,dram__throughput.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,launch__grid_size,launch__block_size > ${f%.ncu-rep}.csv 2>&1; done
+ls -la $O

@@ -39,7 +39,8 @@ NAMES = {
 def emul():
     so = os.path.join(HERE, "host_emul", "libemul.so")
     src = os.path.join(HERE, "host_emul", "emul.cpp")
-    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", so, src])
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", so + ".%d" % os.getpid(), src])
+    os.replace(so + ".%d" % os.getpid(), so)
     return C.CDLL(so)
 
 

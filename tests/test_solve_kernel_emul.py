@@ -22,7 +22,8 @@ def _build(tag, defs):
         return _LIBS[tag]
     so = os.path.join(HERE, "host_emul", f"libsolve_emul_{tag}.so")
     src = os.path.join(HERE, "host_emul", "solve_kernel_emul.cpp")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", "-Wno-unknown-pragmas", *defs, "-shared", "-fPIC", "-o", so, src])
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", "-Wno-unknown-pragmas", *defs, "-shared", "-fPIC", "-o", so + ".%d" % os.getpid(), src])
+    os.replace(so + ".%d" % os.getpid(), so)
     _LIBS[tag] = C.CDLL(so)
     return _LIBS[tag]
 
@@ -56,7 +57,8 @@ def test_emulated_glcm_pipeline_equals_per_voxel_math(kind, n):
     pipe.emul_glcm_pipeline.restype = C.c_longlong
     so = os.path.join(HERE, "host_emul", "libemul_pipe.so")          # own copy: test_host_emul.py rebuilds libemul.so
     if "emul" not in _LIBS:
-        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", so, os.path.join(HERE, "host_emul", "emul.cpp")])
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", so + ".%d" % os.getpid(), os.path.join(HERE, "host_emul", "emul.cpp")])
+        os.replace(so + ".%d" % os.getpid(), so)
         _LIBS["emul"] = C.CDLL(so)
     emul = _LIBS["emul"]
     lev = np.ascontiguousarray(bench.synth_volume(40, kind)[:n, :n, :n].astype(np.uint8))
