@@ -43,6 +43,9 @@ struct GlcmTask {
 #ifndef GF_SOLVE_MINB_L
 #define GF_SOLVE_MINB_L 2
 #endif
+#ifndef GF_LZ_TOPUP
+#define GF_LZ_TOPUP 1              // 0: no topping-up of a size group's last batch with smaller tasks
+#endif
 #ifndef GF_SOLVE_TILE
 #define GF_SOLVE_TILE 4096
 #endif
@@ -172,10 +175,10 @@ glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ 
       // size groups from the top; a group's last batch is topped up with tasks of the next smaller group (a larger N
       // solves them as well: padded nodes), so a tile has ONE partially filled batch instead of three
       const int e14 = bucket[12], e16 = bucket[14], e18 = bucket[15];
-      int s18 = e18 - (e18 - e16 + 127) / 128 * 128;
+      int s18 = GF_LZ_TOPUP ? e18 - (e18 - e16 + 127) / 128 * 128 : e16;
       if (s18 < 0) s18 = 0;
       const int e16b = s18 < e16 ? s18 : e16;
-      int s16 = e16b > e14 ? e16b - (e16b - e14 + 127) / 128 * 128 : e16b;
+      int s16 = !GF_LZ_TOPUP ? e14 : e16b > e14 ? e16b - (e16b - e14 + 127) / 128 * 128 : e16b;
       if (s16 < 0) s16 = 0;
       const int e14b = s16 < e14 ? s16 : e14;
       lanczos_group<18>(lev, P, T, queue, res, order, base, s18, e18, lz_scratch);

@@ -35,7 +35,9 @@ constexpr uint32_t LZ_LOW = 0x36DB6DBu;       // window positions p (a*9 + b*3 +
 #define LZ_EIG_EXACT_STATIC 0      // 1: a task whose node count fills its template takes the fully static eigenvalue search
 #endif
 #ifndef LZ_SEGSUM
-#define LZ_SEGSUM 1                // 1: neighbour sums by a segmented scan over node-sorted endpoint lists (no smem read-modify-write chain)
+#define LZ_SEGSUM 0                // 1: neighbour sums by a segmented scan over node-sorted endpoint lists (no smem read-modify-write
+                                   // chain; bit-identical).  Measured SLOWER on B200 (256^3 uniform GLCM 51.6 vs 47.9 ms): the unrolled
+                                   // 36-entry scan pushes the kernel out of the instruction cache (no_instruction stalls 0.3 -> 2.3 per issue)
 #endif
 constexpr int LZ_ACC = LZ_ACC_N;               // interleaved partial sums per reduction
 constexpr int LZ_NARR = 5;                    // per-thread shared arrays: U, S, IR, D, E (N doubles each)
@@ -326,11 +328,17 @@ RB_HD double glcm_lanczos_axis(const int* wl, const TT& T, double* sm, int st, i
 #pragma unroll
   for (int i = 0; i < N - 1; i++) { d[i] = D[(size_t)i * st]; e[i] = E[(size_t)i * st]; }
   double hi, lo;
+#if LZ_EIG_EXACT_STATIC == 2
+  // always the full static search: padded / broken-down rows are decoupled zero eigenvalues, harmless for max(|hi|,|lo|).
+  // Template-dependent bits: only with GF_LZ_TOPUP=0 (a task's size class then fixes its template)
+  tridiag_extreme_pair_static<N - 1, false>(d, e, &hi, &lo, live && n >= 2);
+#else
 #if LZ_EIG_EXACT_STATIC
   if (n == N) tridiag_extreme_pair_static<N - 1, false>(d, e, &hi, &lo, live);
   else
 #endif
   tridiag_extreme_pair_dyn<N - 1>(d, e, n - 1, &hi, &lo, live && n >= 2);      // the deflated space has n - 1 dimensions
+#endif
   return fmax(fabs(hi), fabs(lo));
 }
 
