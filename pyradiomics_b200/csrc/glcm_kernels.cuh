@@ -44,8 +44,12 @@ struct GlcmTask {
 #define GF_SOLVE_MINB_L 2
 #endif
 #ifndef GF_LZ_TOPUP
-#define GF_LZ_TOPUP 1              // 0: no topping-up of a size group's last batch with smaller tasks
+#define GF_LZ_TOPUP 0              // 1: a size group's last batch is topped up with tasks of the next smaller group (needs
+                                   // LZ_EIG_EXACT_STATIC = 0 for reproducible bits).  Measured on B200, 256^3 GLCM: top-up + task-sized
+                                   // search 48.5 / 96.5 ms (uniform / smooth), no top-up + static search 46.3 / 93.0 ms
 #endif
+static_assert(!(GF_LZ_TOPUP && LZ_EIG_EXACT_STATIC), "topped-up batches need the task-sized eigenvalue search (LZ_EIG_EXACT_STATIC=0): "
+                                                      "otherwise a task's bits depend on the template that happens to solve it");
 #ifndef GF_SOLVE_TILE
 #define GF_SOLVE_TILE 4096
 #endif
@@ -116,7 +120,10 @@ template <int KIND>
 __global__ void __launch_bounds__(128, SolveKind<KIND>::minb)
 glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ VoxParams P,
                        const GlcmFastTables* __restrict__ Tg, const GlcmTask* __restrict__ queue,
-                       const unsigned* __restrict__ qcount, double* __restrict__ res) {
+                       const unsigned* __restrict__ qcount, double* __restrict__ res, int only) {
+  // only = 0: every size group of this kind; else just the group of that template size (one launch per group keeps ONE
+  // solver body in the instruction cache at a time: ncu showed 7 no_instruction stall cycles per issue on smooth volumes,
+  // where the blocks of an SM sit in different groups)
   __shared__ GlcmSolveTables T;
   if (threadIdx.x == 0) glcm_solve_tables_from(*Tg, T);
   __syncthreads();
@@ -181,20 +188,20 @@ glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ 
       int s16 = !GF_LZ_TOPUP ? e14 : e16b > e14 ? e16b - (e16b - e14 + 127) / 128 * 128 : e16b;
       if (s16 < 0) s16 = 0;
       const int e14b = s16 < e14 ? s16 : e14;
-      lanczos_group<18>(lev, P, T, queue, res, order, base, s18, e18, lz_scratch);
-      lanczos_group<16>(lev, P, T, queue, res, order, base, s16, e16b, lz_scratch);
-      lanczos_group<14>(lev, P, T, queue, res, order, base, 0, e14b, lz_scratch);
+      if (!only || only == 18) lanczos_group<18>(lev, P, T, queue, res, order, base, s18, e18, lz_scratch);
+      if (!only || only == 16) lanczos_group<16>(lev, P, T, queue, res, order, base, s16, e16b, lz_scratch);
+      if (!only || only == 14) lanczos_group<14>(lev, P, T, queue, res, order, base, 0, e14b, lz_scratch);
     } else {
       // dense solves: one template size at a time, block-uniform (idle threads run on an empty window), so the
       // barriers inside glcm_small_solve keep the warps on the same code (ncu: 8-10 no_instruction stall cycles
       // per issue with free-running warps -- these bodies are 2-10 k straight-line instructions)
       if (KIND == 0) {
-        solve_group<4>(lev, P, T, queue, res, order, base, 0, bucket[2]);
-        solve_group<6>(lev, P, T, queue, res, order, base, bucket[2], bucket[4]);
-        solve_group<8>(lev, P, T, queue, res, order, base, bucket[4], bucket[6]);
+        if (!only || only == 4) solve_group<4>(lev, P, T, queue, res, order, base, 0, bucket[2]);
+        if (!only || only == 6) solve_group<6>(lev, P, T, queue, res, order, base, bucket[2], bucket[4]);
+        if (!only || only == 8) solve_group<8>(lev, P, T, queue, res, order, base, bucket[4], bucket[6]);
       } else {
-        solve_group<10>(lev, P, T, queue, res, order, base, 0, bucket[8]);
-        solve_group<12>(lev, P, T, queue, res, order, base, bucket[8], bucket[GF_DENSE_MAX_CLS]);
+        if (!only || only == 10) solve_group<10>(lev, P, T, queue, res, order, base, 0, bucket[8]);
+        if (!only || only == 12) solve_group<12>(lev, P, T, queue, res, order, base, bucket[8], bucket[GF_DENSE_MAX_CLS]);
       }
     }
     __syncthreads();

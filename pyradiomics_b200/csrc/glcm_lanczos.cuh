@@ -32,7 +32,9 @@ constexpr uint32_t LZ_LOW = 0x36DB6DBu;       // window positions p (a*9 + b*3 +
 #define LZ_ACC_N 3
 #endif
 #ifndef LZ_EIG_EXACT_STATIC
-#define LZ_EIG_EXACT_STATIC 0      // 1: a task whose node count fills its template takes the fully static eigenvalue search
+#define LZ_EIG_EXACT_STATIC 2      // 2: always the fully static eigenvalue search of the template's (N-1) x (N-1) tridiagonal (default,
+                                   // with GF_LZ_TOPUP = 0); 0: search sized by the task (template-independent bits: needed when
+                                   // batches are topped up across size groups); 1: static only when the task fills its template
 #endif
 #ifndef LZ_SEGSUM
 #define LZ_SEGSUM 0                // 1: neighbour sums by a segmented scan over node-sorted endpoint lists (no smem read-modify-write

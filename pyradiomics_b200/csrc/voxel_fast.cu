@@ -16,6 +16,9 @@
 
 namespace rb {
 
+#ifndef GF_SOLVE_SPLIT
+#define GF_SOLVE_SPLIT 0
+#endif
 #ifndef GF_PHASEA_NT
 #define GF_PHASEA_NT 512
 #endif
@@ -126,15 +129,26 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
     else glcm_fast_kernel<1, 256><<<grid, 256, glcm_phaseA_smem_bytes(256), st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
     RB_LAUNCH_CHECK();
     static const int solve_bps = getenv("B200_GLCM_SOLVE_BPS") ? atoi(getenv("B200_GLCM_SOLVE_BPS")) : 8;
-    glcm_fast_solve_kernel<0><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
-    glcm_fast_solve_kernel<1><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
+    // B200_GLCM_SPLIT bit 0: one launch per Lanczos size group, bit 1: one launch per dense size group (A/B switch)
+    static const int split = getenv("B200_GLCM_SPLIT") ? atoi(getenv("B200_GLCM_SPLIT")) : GF_SOLVE_SPLIT;
+    if (split & 2) {
+      for (int g = 4; g <= 8; g += 2) glcm_fast_solve_kernel<0><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res, g);
+      for (int g = 10; g <= 12; g += 2) glcm_fast_solve_kernel<1><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res, g);
+    } else {
+      glcm_fast_solve_kernel<0><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res, 0);
+      glcm_fast_solve_kernel<1><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res, 0);
+    }
     // register Lanczos: 90 KB of per-thread shared vectors per CTA -> two CTAs per SM
     static bool lz_attr[64] = {false};
     if (!lz_attr[dev & 63]) {
       RB_CUDA(cudaFuncSetAttribute(glcm_fast_solve_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_LZ_SMEM_BYTES));
       lz_attr[dev & 63] = true;
     }
-    glcm_fast_solve_kernel<2><<<sms * 2, 128, GF_LZ_SMEM_BYTES, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res);
+    if (split & 1) {
+      for (int g = 18; g >= 14; g -= 2) glcm_fast_solve_kernel<2><<<sms * 2, 128, GF_LZ_SMEM_BYTES, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res, g);
+    } else {
+      glcm_fast_solve_kernel<2><<<sms * 2, 128, GF_LZ_SMEM_BYTES, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res, 0);
+    }
     RB_LAUNCH_CHECK();
     glcm_fast_finish_kernel<<<sms * 8, 256, 0, st>>>(P, Q->q, Q->count, Q->res, out + (long long)G_MCC * fstride, out_z0);
     RB_LAUNCH_CHECK();

@@ -1,5 +1,5 @@
 # per-kernel durations (ncu, single metric) of one GLCM call: scripts/launch_list.sh SIZE KIND OUT.csv
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:glcm_fast --launch-skip 25 -c 25 --csv --log-file $3 python scripts/prof_glcm.py $1 $2 glcm > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:glcm_fast --launch-skip ${4:-25} -c ${4:-25} --csv --log-file $3 python scripts/prof_glcm.py $1 $2 glcm > /dev/null 2>&1
 python - "$3" <<'PY'
 import csv, sys, collections
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 5]

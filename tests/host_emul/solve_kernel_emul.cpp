@@ -66,7 +66,7 @@ static void run_kind(const uint8_t* lev, const VoxParams& P, const GlcmFastTable
     for (unsigned t = 0; t < 128; t++)
       th.emplace_back([=, &cnt]() {
         threadIdx = {t, 0, 0};
-        glcm_fast_solve_kernel<KIND>(lev, P, T, q, &cnt, res);
+        glcm_fast_solve_kernel<KIND>(lev, P, T, q, &cnt, res, 0);
       });
     for (auto& x : th) x.join();
     pthread_barrier_destroy(&g_barrier);
@@ -158,9 +158,10 @@ extern "C" long long emul_glcm_pipeline(const uint8_t* lev, int Z, int Y, int X,
     GlcmTask* qp = q.data(); double* rp = res.data(); unsigned* cp = &count;
     emu_launch(3, 256, [=]() { glcm_fast_kernel<1, 256>(lev, nullptr, P, T, out, fstride, za, zb, 0, qp, cp); });
     for (unsigned k = 0; k < count; k++) res[k] = -12345.0;
-    emu_launch(2, 128, [=]() { glcm_fast_solve_kernel<0>(lev, P, T, qp, cp, rp); });
-    emu_launch(2, 128, [=]() { glcm_fast_solve_kernel<1>(lev, P, T, qp, cp, rp); });
-    emu_launch(2, 128, [=]() { glcm_fast_solve_kernel<2>(lev, P, T, qp, cp, rp); });
+    // one launch per size group, as voxel_fast.cu does with B200_GLCM_SPLIT=3 (dense kinds) / the whole kind at once
+    for (int g = 4; g <= 8; g += 2) emu_launch(2, 128, [=]() { glcm_fast_solve_kernel<0>(lev, P, T, qp, cp, rp, g); });
+    emu_launch(2, 128, [=]() { glcm_fast_solve_kernel<1>(lev, P, T, qp, cp, rp, 0); });
+    for (int g = 18; g >= 14; g -= 2) emu_launch(2, 128, [=]() { glcm_fast_solve_kernel<2>(lev, P, T, qp, cp, rp, g); });
     emu_launch(2, 256, [=]() { glcm_fast_finish_kernel(P, qp, cp, rp, out + (long long)G_MCC * fstride, 0); });
     total_tasks += count;
   }
