@@ -17,7 +17,7 @@
 namespace rb {
 
 #ifndef GF_SOLVE_SPLIT
-#define GF_SOLVE_SPLIT 0
+#define GF_SOLVE_SPLIT 3
 #endif
 #ifndef GF_PHASEA_NT
 #define GF_PHASEA_NT 512
@@ -129,13 +129,20 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
     else glcm_fast_kernel<1, 256><<<grid, 256, glcm_phaseA_smem_bytes(256), st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
     RB_LAUNCH_CHECK();
     static const int solve_bps = getenv("B200_GLCM_SOLVE_BPS") ? atoi(getenv("B200_GLCM_SOLVE_BPS")) : 8;
-    // B200_GLCM_SPLIT bit 0: one launch per Lanczos size group, bit 1: one launch per dense size group (A/B switch)
+    // One launch per size group keeps ONE solver body in the instruction cache (the three Lanczos templates together are
+    // 18.5 k SASS instructions, 296 KB; ncu: 7.2 no_instruction stall cycles per issue on a smooth volume, whose blocks sit
+    // in different groups).  256^3 smooth, ncu launch list: Lanczos 30.1 -> 20.5 ms, dense n <= 12 16.9 -> 15.3 ms, dense
+    // n <= 8 11.9 -> 12.4 ms (so that one stays a single launch); uniform volume: +0.2 ms of repeated tile sorts.
+    // B200_GLCM_SPLIT: bit 0 Lanczos, bit 1 dense <= 12, bit 2 dense <= 8 (A/B switch).
     static const int split = getenv("B200_GLCM_SPLIT") ? atoi(getenv("B200_GLCM_SPLIT")) : GF_SOLVE_SPLIT;
-    if (split & 2) {
+    if (split & 4) {
       for (int g = 4; g <= 8; g += 2) glcm_fast_solve_kernel<0><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res, g);
-      for (int g = 10; g <= 12; g += 2) glcm_fast_solve_kernel<1><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res, g);
     } else {
       glcm_fast_solve_kernel<0><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res, 0);
+    }
+    if (split & 2) {
+      for (int g = 10; g <= 12; g += 2) glcm_fast_solve_kernel<1><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res, g);
+    } else {
       glcm_fast_solve_kernel<1><<<sms * solve_bps, 128, 0, st>>>((const uint8_t*)lev, P, T, Q->q, Q->count, Q->res, 0);
     }
     // register Lanczos: 90 KB of per-thread shared vectors per CTA -> two CTAs per SM
