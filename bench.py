@@ -394,6 +394,7 @@ def plugin_e2e(ctx, vol, steps, map_dtype="float64"):
     return {"value": float(np.prod(vol.shape)) / dt, "unit": "voxels/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": steps, "maps": nmaps, "map_dtype": map_dtype,
             "d2h_gb_per_s_per_rank": d2h / ctx.world / dt / 1e9, "first_value_probe": probe,
+            "scaling": "strong: ONE image per step, its z-slabs on the N GPUs" if ctx.world > 1 else "one image on one GPU",
             "api": "pyradiomics_b200.featureclasses.Radiomics{GLCM,GLRLM,GLSZM,GLDM,NGTDM}(raw int16 image, mask, voxelBased=True, "
                    "binWidth=25, b200_image_key=<step id>).execute(): H2D, discretisation once per image, fused kernels, chunked D2H into "
                    "page-locked maps; N > 1: every rank gets the whole host image and returns its z-slab (b200_zrange); max over ranks"}
@@ -465,24 +466,26 @@ def secondary_config5ii(ctx, ncases=64, n=256):
         lev = torch.randint(1, 33, (n, n, n), generator=g, device=ctx.dev, dtype=torch.int16)
         return ((lev - 1) * 25 + 3).cpu().numpy()
 
-    def run(raw):
+    def run(raw, k):
         FC.clear_device_cache()
-        return {c: FC.FEATURE_CLASSES[c](raw, mask, binWidth=25).execute() for c in CLASSES}
+        # b200_image_key: the case id names the image for the five classes of one case (else each class hashes its content)
+        return {c: FC.FEATURE_CLASSES[c](raw, mask, binWidth=25, b200_image_key=("case", k)).execute() for c in CLASSES}
 
-    run(case(ncases))                                   # warm-up
+    run(case(ncases), ncases)                           # warm-up
     raws = [case(k) for k in mine]
     ctx.barrier()
     t0 = time.perf_counter()
     nfeat = 0
-    for raw in raws:
-        nfeat = sum(len(v) for v in run(raw).values())
+    for k, raw in zip(mine, raws):
+        nfeat = sum(len(v) for v in run(raw, k).values())
     torch.cuda.synchronize()
     dt = ctx.max_over_ranks(time.perf_counter() - t0)
     return {"workload": f"batch of {ncases} independent synthetic {n}^3 cases, segment-based full suite ({nfeat} features per case), "
                         f"cases sharded round-robin over {ctx.world} GPU(s), no collective",
             "cases": ncases, "seconds": dt, "cases_per_s": ncases / dt, "value": ncases * float(n) ** 3 / dt, "unit": "voxels/s",
             "ms_per_case_per_gpu": 1e3 * dt / max(1, len(mine)),
-            "api": "Radiomics{GLCM,GLRLM,GLSZM,GLDM,NGTDM}(raw int16 image, mask, binWidth=25).execute() per case (host buffers)"}
+            "api": "Radiomics{GLCM,GLRLM,GLSZM,GLDM,NGTDM}(raw int16 image, mask, binWidth=25, b200_image_key=<case id>).execute() per case "
+                   "(host buffers)"}
 
 
 def run_b200(args):

@@ -128,7 +128,7 @@ glcm_fast_solve_kernel(const uint8_t* __restrict__ lev, const __grid_constant__ 
   if (threadIdx.x == 0) glcm_solve_tables_from(*Tg, T);
   __syncthreads();
   const unsigned n = *qcount;
-  // Tiles of GF_SOLVE_TILE (2048) consecutive tasks are counting-sorted by size class in shared memory, so the
+  // Tiles of GF_SOLVE_TILE (4096) consecutive tasks are counting-sorted by size class in shared memory, so the
   // lanes of a warp run solves of the same size (ncu: 11-14 of 32 lanes active otherwise).  The sort is STABLE and
   // atomic-free (per-thread counts, one serial scan per class), so the position of a task -- and with it the batch and,
   // for topped-up Lanczos batches, the size template that solves it -- is the same in every run: bit-reproducible maps.

@@ -39,6 +39,46 @@ def _dev():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_TORCH_OF_NP = {np.int16: torch.int16, np.int32: torch.int32, np.float32: torch.float32, np.float64: torch.float64,
+                np.uint8: torch.uint8, np.int64: torch.int64}
+_STAGE = {"bufs": None, "pool": None}
+_STAGE_CHUNK = 32 << 20
+_STAGE_MIN = 64 << 20
+
+
+def _upload_staged(a):
+    """pageable NumPy array -> CUDA tensor through two page-locked 32 MB staging blocks: a few threads copy chunk k+1 into
+    one block (NumPy releases the GIL) while the DMA engine drains chunk k from the other.  A plain ``tensor.to(device)`` of
+    pageable memory lets the driver stage single-threaded (~10 GB/s: 40 ms for the 0.4 GB of a 512^3 image + mask, which
+    is a quarter of a rank's step when eight GPUs share one image)."""
+    import concurrent.futures as cf
+    flat = a.reshape(-1).view(np.uint8)
+    n = flat.size
+    dev = _dev()
+    out = torch.empty(n, dtype=torch.uint8, device=dev)
+    if _STAGE["bufs"] is None:
+        _STAGE["bufs"] = [torch.empty(_STAGE_CHUNK, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+        _STAGE["pool"] = cf.ThreadPoolExecutor(max_workers=4)
+    bufs, pool = _STAGE["bufs"], _STAGE["pool"]
+    views = [b.numpy() for b in bufs]
+    done = [None, None]
+    stream = torch.cuda.current_stream()
+    for k, off in enumerate(range(0, n, _STAGE_CHUNK)):
+        m = min(_STAGE_CHUNK, n - off)
+        j = k & 1
+        if done[j] is not None:
+            done[j].synchronize()                   # the DMA out of this block has finished
+        q = (m + 3) // 4
+        list(pool.map(lambda s: np.copyto(views[j][s:min(s + q, m)], flat[off + s:off + min(s + q, m)]), range(0, m, q)))
+        out[off:off + m].copy_(bufs[j][:m], non_blocking=True)
+        done[j] = torch.cuda.Event()
+        done[j].record(stream)
+    for e in done:
+        if e is not None:
+            e.synchronize()                         # the staging blocks are reused by the next upload
+    return out.view(_TORCH_OF_NP[a.dtype.type]).reshape(a.shape)
+
+
 def _to_device(arr):
     """NumPy / torch -> contiguous CUDA tensor of a supported dtype (uint16 travels as int32)."""
     if isinstance(arr, torch.Tensor):
@@ -55,7 +95,10 @@ def _to_device(arr):
         a = a.astype(np.int32)
     elif a.dtype not in _DT:
         a = a.astype(np.float64)
-    return torch.from_numpy(np.ascontiguousarray(a)).to(_dev())
+    a = np.ascontiguousarray(a)
+    if a.nbytes >= _STAGE_MIN and a.dtype.type in _TORCH_OF_NP:
+        return _upload_staged(a)
+    return torch.from_numpy(a).to(_dev())
 
 
 def _decode_key(k: int) -> float:

@@ -428,3 +428,18 @@ def test_log_x_axis_tiles_match_restatement_on_ragged_sizes():
                 cur = FN.recursive_gaussian_axis(cur, IO.recursive_gaussian_coefficients(1.5, 0), e).astype(np.float32).astype(np.float64)
         ref += (FN.recursive_gaussian_axis(cur, IO.recursive_gaussian_coefficients(1.5, 2), d) * 1.5 ** 2).astype(np.float32)
     assert np.allclose(out, ref, rtol=2e-4, atol=2e-4 * np.abs(ref).max())
+
+
+@pytest.mark.gpu
+def test_staged_upload_of_large_host_arrays_is_exact():
+    """imageoperations._to_device stages big pageable arrays through page-locked blocks with copy threads"""
+    from pyradiomics_b200 import imageoperations as IO
+    rng = np.random.default_rng(3)
+    for dt, shape in ((np.int16, (97, 613, 611)), (np.uint8, (70 * (1 << 20) + 13,)), (np.float64, (9, 1031, 1033))):
+        a = rng.integers(0, 200, shape).astype(dt)
+        assert a.nbytes >= IO._STAGE_MIN
+        t = IO._to_device(a)
+        assert tuple(t.shape) == a.shape
+        np.testing.assert_array_equal(t.cpu().numpy(), a)
+    b = rng.random((64, 64, 64))                        # small arrays take the plain path
+    np.testing.assert_array_equal(IO._to_device(b).cpu().numpy(), b)
