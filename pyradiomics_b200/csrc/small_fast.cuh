@@ -212,20 +212,31 @@ struct GlszmAcc {
 };
 
 RB_HD void glszm_fast_voxel(const int* wl, const SmallFastTables& T, double* out) {
+  // equality masks of the window (as the other fast paths).  A level that occurs ONCE is one zone of size 1: its share
+  // of every sum is added in the static loop below (27 i.i.d. levels out of 32: ~12 such levels); only the levels that
+  // occur at least twice (<= 13 of them, ~7) go through the flood fill.
+  uint32_t eq[27];
+  RB_EQMASKS_27(wl, eq);
   uint32_t M = 0;
-  int wd[27];                         // copy for data-dependent indexing (the seed voxel of a level)
+  uint32_t cls[13];
+  int clg[13];
+  int nl = 0, S_n = 0, S_g = 0, S_g2 = 0;
+  double S_ig = 0;
 #pragma unroll
-  for (int v = 0; v < 27; v++) { wd[v] = wl[v]; if (wl[v]) M |= 1u << v; }
+  for (int v = 0; v < 27; v++) {
+    if (wl[v]) M |= 1u << v;
+    if (eq[v] && (eq[v] & ((1u << v) - 1)) == 0) {
+      if (eq[v] == (1u << v)) { S_n++; S_g += wl[v]; S_g2 += wl[v] * wl[v]; S_ig += T.inv2[wl[v]]; }
+      else { cls[nl] = eq[v]; clg[nl] = wl[v]; nl++; }
+    }
+  }
   GlszmAcc a;
-  a.Nz = a.Sg = a.Sg2 = a.Ss2 = a.X4 = a.gln = 0;
-  a.A = a.Sinv = a.X1 = a.X2 = a.X3 = a.lg = 0;
-  a.h0 = a.h1 = a.h2 = 0;
-  for (uint32_t rem = M; rem;) {
-    const int g = wd[RB_CTZ(rem)], g2 = g * g;       // next level not handled yet
-    uint32_t m = 0;
-#pragma unroll
-    for (int u = 0; u < 27; u++) m |= (uint32_t)(wl[u] == g) << u;
-    rem &= ~m;
+  a.Nz = S_n; a.Sg = S_g; a.Sg2 = S_g2; a.Ss2 = S_n; a.X4 = S_g2; a.gln = S_n;
+  a.A = S_ig; a.Sinv = (double)S_n; a.X1 = S_ig; a.X2 = (double)S_g2; a.X3 = S_ig; a.lg = 0;
+  a.h0 = (unsigned long long)S_n; a.h1 = a.h2 = 0;
+  for (int k = 0; k < nl; k++) {
+    const int g = clg[k], g2 = g * g;
+    uint32_t m = cls[k];
     const double ig = T.inv2[g];
     int zs[8];                                         // <= 8 mutually non-adjacent zones fit a 3x3x3 window
     int zc = 0;

@@ -121,10 +121,14 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
     if (!pa_attr[dev & 63]) {
       RB_CUDA(cudaFuncSetAttribute(glcm_fast_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, glcm_phaseA_smem_bytes(256)));
       RB_CUDA(cudaFuncSetAttribute(glcm_fast_kernel<1, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, glcm_phaseA_smem_bytes(384)));
+      RB_CUDA(cudaFuncSetAttribute(glcm_fast_kernel<1, 640>, cudaFuncAttributeMaxDynamicSharedMemorySize, glcm_phaseA_smem_bytes(640)));
+      RB_CUDA(cudaFuncSetAttribute(glcm_fast_kernel<1, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, glcm_phaseA_smem_bytes(768)));
       RB_CUDA(cudaFuncSetAttribute(glcm_fast_kernel<1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, glcm_phaseA_smem_bytes(512)));
       pa_attr[dev & 63] = true;
     }
     if (nt == 512) glcm_fast_kernel<1, 512><<<grid, 512, glcm_phaseA_smem_bytes(512), st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
+    else if (nt == 640) glcm_fast_kernel<1, 640><<<grid, 640, glcm_phaseA_smem_bytes(640), st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
+    else if (nt == 768) glcm_fast_kernel<1, 768><<<grid, 768, glcm_phaseA_smem_bytes(768), st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
     else if (nt == 384) glcm_fast_kernel<1, 384><<<grid, 384, glcm_phaseA_smem_bytes(384), st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
     else glcm_fast_kernel<1, 256><<<grid, 256, glcm_phaseA_smem_bytes(256), st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
     RB_LAUNCH_CHECK();
