@@ -366,6 +366,8 @@ def plugin_e2e(ctx, vol, steps, map_dtype="float64"):
         kw["b200_zrange"] = (z0, z1)
     step_no = [0]
 
+    phases = {}
+
     def one():
         FC.clear_device_cache()                    # every step pays the H2D + discretisation of its image
         step_no[0] += 1
@@ -373,11 +375,19 @@ def plugin_e2e(ctx, vol, steps, map_dtype="float64"):
         # the first class uploads and bins, the other four find it by that key instead of re-hashing 400 MB each
         kw["b200_image_key"] = ("bench", map_dtype, step_no[0])
         maps = {}
-        for c in ("gldm", "glszm", "glrlm", "ngtdm", "glcm"):
-            maps[c] = FC.FEATURE_CLASSES[c](raw, mask, **kw).execute()
+        for k, c in enumerate(("gldm", "glszm", "glrlm", "ngtdm", "glcm")):
+            ta = time.perf_counter()
+            obj = FC.FEATURE_CLASSES[c](raw, mask, **kw)
+            tb = time.perf_counter()
+            maps[c] = obj.execute()
+            tc = time.perf_counter()
+            if k == 0:
+                phases["image_h2d_bin"] = phases.get("image_h2d_bin", 0.0) + (tb - ta)
+            phases[c] = phases.get(c, 0.0) + (tc - tb)
         return maps
 
     m = one()                                        # warm-up: faults the page-locked blocks in, builds the tables
+    phases.clear()
     nmaps = sum(len(v) for v in m.values())
     probe = float(np.asarray(next(iter(m["glcm"].values())).array).ravel()[0])
     del m
@@ -394,6 +404,7 @@ def plugin_e2e(ctx, vol, steps, map_dtype="float64"):
     return {"value": float(np.prod(vol.shape)) / dt, "unit": "voxels/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": steps, "maps": nmaps, "map_dtype": map_dtype,
             "d2h_gb_per_s_per_rank": d2h / ctx.world / dt / 1e9, "first_value_probe": probe,
+            "phases_ms_rank0": {k: round(1e3 * v / steps, 2) for k, v in phases.items()},
             "scaling": "strong: ONE image per step, its z-slabs on the N GPUs" if ctx.world > 1 else "one image on one GPU",
             "api": "pyradiomics_b200.featureclasses.Radiomics{GLCM,GLRLM,GLSZM,GLDM,NGTDM}(raw int16 image, mask, voxelBased=True, "
                    "binWidth=25, b200_image_key=<step id>).execute(): H2D, discretisation once per image, fused kernels, chunked D2H into "

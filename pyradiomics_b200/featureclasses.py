@@ -323,6 +323,12 @@ class RadiomicsFeaturesBase:
             raise ValueError("b200_map_dtype must be 'float64' (the reference's map type) or 'float32'")
         return torch.float64 if dt == "float64" else torch.float32
 
+    def _zchunk(self, nz):
+        """planes per chunk of the compute / copy pipeline: ``b200_zchunk``, else a sixteenth of the planes within [8, 64] --
+        a rank that holds 64 planes of an image shared by eight GPUs still overlaps its kernels with its PCIe copies"""
+        zc = int(self.settings.get("b200_zchunk", 0) or 0)
+        return zc if zc > 0 else max(8, min(64, -(-nz // 16)))
+
     def _calculateVoxels(self):
         """The fused kernel of the class in z-chunks; the ENABLED maps stream to page-locked host memory chunk by
         chunk while the next chunk computes (voxel.class_maps_to_host) -- replaces the voxelBatch loop and the
@@ -345,7 +351,7 @@ class RadiomicsFeaturesBase:
         with self.progressReporter(total=int(z1 - z0), desc="planes") as pbar:
             host = voxel.class_maps_to_host(self.CLASS, lev, settings, idx, centers=centers, alive=alive, status=status,
                                             z0=int(z0), z1=int(z1),
-                                            zchunk=int(self.settings.get("b200_zchunk", 64)), out_dtype=self._map_dtype(),
+                                            zchunk=self._zchunk(int(z1 - z0)), out_dtype=self._map_dtype(),
                                             progress=pbar.update)
         st = int(status.item())
         if st & 2:
