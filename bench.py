@@ -548,15 +548,17 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = ALG_BYTES[dom] * (nz * Z * Z) / (per_class_ms[dom] * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
         if prof.get("kernel_class") == dom and prof.get("voxels"):
             traffic = prof["dram_bytes_per_launch"] * (nz * Z * Z) / prof["voxels"]
+            traffic_src = "profiles/roofline_traffic.json: ncu dram bytes of one plane chunk, scaled by voxels (%.0f B/voxel)" % (
+                prof["dram_bytes_per_launch"] / prof["voxels"])
     except (OSError, ValueError, KeyError):
         pass
     roofline = {"bound": "hbm", "kernel": f"{dom} fused voxel kernels", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "ms_per_launch": per_class_ms[dom], "per_class_ms": per_class_ms,
                 "suite_frac": 625.0 * value / ctx.world / 1e9 / peak,

@@ -39,3 +39,15 @@ def test_bench_voxel_sampler_hits_faces_edges_and_corners():
     on_border = ((v == 0) | (v == 63)).sum(0)
     assert (on_border >= 1).mean() > 0.15 and (on_border >= 2).sum() > 50 and (on_border == 3).sum() > 5
     assert np.array_equal(bench.raw_from_levels(np.array([1, 2, 32])), np.array([3, 28, 778], np.int16))
+
+
+def test_plugin_zchunk_keeps_a_thin_slab_pipelined():
+    """the compute / copy pipeline of a class needs several chunks per call: a sixteenth of the planes within [8, 64]
+    unless the caller fixes b200_zchunk"""
+    from pyradiomics_b200 import featureclasses as FC
+    obj = FC.RadiomicsGLCM.__new__(FC.RadiomicsGLCM)
+    obj.settings = {}
+    assert [obj._zchunk(n) for n in (512, 256, 64, 20, 1)] == [32, 16, 8, 8, 8]
+    assert obj._zchunk(4096) == 64
+    obj.settings = {"b200_zchunk": 5}
+    assert obj._zchunk(512) == 5
