@@ -64,7 +64,10 @@ const char *rb_version(void);
 int rb_device_count(void);          /* >= 0, or RB_ERR_CUDA                                   */
 int rb_num_features(int cls);       /* 24 / 16 / 16 / 14 / 5                                  */
 /* The fused GLCM path keeps one eigen-task queue per (device, stream) it ran on (grown on demand, up to 1.15 GB) so that
- * repeated calls do not reallocate; this synchronises the current device and frees its queues. */
+ * repeated calls do not reallocate; this synchronises the current device and frees its queues.  Threading contract of
+ * the library: calls on DIFFERENT streams may run from different host threads (each stream owns its queue; the cache map
+ * is mutex-protected); two host threads must not issue GLCM calls on the SAME stream at once, nor call this function while
+ * another thread has a call in flight on this device. */
 int rb_release_device_caches(void);
 /* name of feature `idx` of class `cls` (the reference's get<Name>FeatureValue names, in the
  * alphabetical order in which the reference enumerates them, radiomics/base.py:163-179). */
