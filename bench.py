@@ -142,7 +142,9 @@ def run_reference(args):
     vol = synth_volume(args.size, args.kind)
     kind = cpu_arm_setup(vol)
     cores = min(os.cpu_count() or 1, args.cpu_workers)
-    per_worker = args.cpu_voxels_per_worker
+    # bounded sample per step, sized so that the whole run stays within a few minutes whatever --steps is: at most
+    # ~8 x cpu_voxels_per_worker voxels per worker over all timed steps (the rate does not depend on the batch size)
+    per_worker = max(16, min(args.cpu_voxels_per_worker, (8 * args.cpu_voxels_per_worker) // max(1, args.steps)))
     pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
     for w in range(args.warmup):
         cpu_arm_step(vol, cores, max(8, per_worker // 8), 100 + w, pool)
