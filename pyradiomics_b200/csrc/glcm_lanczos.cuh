@@ -34,7 +34,8 @@ constexpr uint32_t LZ_LOW = 0x36DB6DBu;       // window positions p (a*9 + b*3 +
 #ifndef LZ_EIG_EXACT_STATIC
 #define LZ_EIG_EXACT_STATIC 2      // 2: always the fully static eigenvalue search of the template's (N-1) x (N-1) tridiagonal (default,
                                    // with GF_LZ_TOPUP = 0); 0: search sized by the task (template-independent bits: needed when
-                                   // batches are topped up across size groups); 1: static only when the task fills its template
+                                   // batches are topped up across size groups).  (A mixed mode -- static only for tasks that fill
+                                   // their template -- measured slower: divergent lanes run both searches.)
 #endif
 #ifndef LZ_SEGSUM
 #define LZ_SEGSUM 0                // 1: neighbour sums by a segmented scan over node-sorted endpoint lists (no smem read-modify-write
@@ -335,10 +336,6 @@ RB_HD double glcm_lanczos_axis(const int* wl, const TT& T, double* sm, int st, i
   // Template-dependent bits: only with GF_LZ_TOPUP=0 (a task's size class then fixes its template)
   tridiag_extreme_pair_static<N - 1, false>(d, e, &hi, &lo, live && n >= 2);
 #else
-#if LZ_EIG_EXACT_STATIC
-  if (n == N) tridiag_extreme_pair_static<N - 1, false>(d, e, &hi, &lo, live);
-  else
-#endif
   tridiag_extreme_pair_dyn<N - 1>(d, e, n - 1, &hi, &lo, live && n >= 2);      // the deflated space has n - 1 dimensions
 #endif
   return fmax(fabs(hi), fabs(lo));

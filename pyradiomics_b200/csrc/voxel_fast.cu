@@ -111,7 +111,8 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
     RB_CUDA(cudaMemsetAsync(Q->count, 0, sizeof(unsigned), st));
     // phase A: one CTA per SM (register-bound).  512 threads at 128 registers (a hundred spilled words per thread, L1-
     // resident) put 16 warps on an SM instead of the 8 of the 256-thread / 236-register build: measured 50.6 vs 62.5 ms
-    // per 256^3 (uniform), 104.7 vs 117.5 (smooth); 384 threads / 168 registers sit in between.  B200_GLCM_NT selects
+    // per 256^3 (uniform), 104.7 vs 117.5 (smooth); 384 threads / 168 registers sit in between; 640 / 768 threads at 96 / 80
+    // registers (344 / 408 B of spills per thread) measured the same as 512 and were dropped again.  B200_GLCM_NT selects
     // the variant for A/B runs.
     static const int nt = getenv("B200_GLCM_NT") ? atoi(getenv("B200_GLCM_NT")) : GF_PHASEA_NT;
     const uint8_t* l8 = (const uint8_t*)lev;
@@ -121,14 +122,10 @@ int glcm_fast_launch(const void* lev, const uint8_t* centers, const VoxParams& P
     if (!pa_attr[dev & 63]) {
       RB_CUDA(cudaFuncSetAttribute(glcm_fast_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, glcm_phaseA_smem_bytes(256)));
       RB_CUDA(cudaFuncSetAttribute(glcm_fast_kernel<1, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, glcm_phaseA_smem_bytes(384)));
-      RB_CUDA(cudaFuncSetAttribute(glcm_fast_kernel<1, 640>, cudaFuncAttributeMaxDynamicSharedMemorySize, glcm_phaseA_smem_bytes(640)));
-      RB_CUDA(cudaFuncSetAttribute(glcm_fast_kernel<1, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, glcm_phaseA_smem_bytes(768)));
       RB_CUDA(cudaFuncSetAttribute(glcm_fast_kernel<1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, glcm_phaseA_smem_bytes(512)));
       pa_attr[dev & 63] = true;
     }
     if (nt == 512) glcm_fast_kernel<1, 512><<<grid, 512, glcm_phaseA_smem_bytes(512), st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
-    else if (nt == 640) glcm_fast_kernel<1, 640><<<grid, 640, glcm_phaseA_smem_bytes(640), st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
-    else if (nt == 768) glcm_fast_kernel<1, 768><<<grid, 768, glcm_phaseA_smem_bytes(768), st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
     else if (nt == 384) glcm_fast_kernel<1, 384><<<grid, 384, glcm_phaseA_smem_bytes(384), st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
     else glcm_fast_kernel<1, 256><<<grid, 256, glcm_phaseA_smem_bytes(256), st>>>(l8, centers, P, T, out, fstride, za, zb, out_z0, Q->q, Q->count);
     RB_LAUNCH_CHECK();
