@@ -300,6 +300,10 @@ def measure_suite(ctx, vol, steps, warmup, classes=CLASSES, oracle=None, check_d
     launches = [0]
     zchunk = max(1, (48 << 20) // (vol.shape[1] * vol.shape[2] * 13))
     glcm_chunks = -(-nz // zchunk)
+    # kernels per plane chunk of a GLCM call: phase A, the eigen-solve kernels (one launch per size group where that is the
+    # default: voxel_fast.cu GF_SOLVE_SPLIT = 3 -> dense <= 8: 1, dense <= 12: 2, Lanczos: 3), finish
+    split = int(os.environ.get("B200_GLCM_SPLIT", "3"))
+    glcm_per_chunk = 1 + (3 if split & 4 else 1) + (2 if split & 2 else 1) + (3 if split & 1 else 1) + 1
 
     def step(record):
         slab.exchange()
@@ -313,7 +317,7 @@ def measure_suite(ctx, vol, steps, warmup, classes=CLASSES, oracle=None, check_d
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             voxel.voxel_features(c, buf, settings, z0=r, z1=r + nz, out=outs[c], out_z0=r, alive=alive)
-            launches[0] += 5 * glcm_chunks if c == "glcm" else 1   # per plane chunk: phase A, 3 eigen-solve kernels, finish
+            launches[0] += glcm_per_chunk * glcm_chunks if c == "glcm" else 1
             if record:
                 e1.record()
                 ev[c].append((e0, e1))
