@@ -106,8 +106,39 @@ def voxel_volumes():
     return vols
 
 
-def voxel_goldens():
-    for name, v in voxel_volumes().items():
+def voxel_volumes_extra():
+    """more settings variants, added at the end of round 2 (`--voxel-extra-only` -> voxelx_*.npz).  They pin the oracle and
+    the host-compiled device math (tests/test_oracle.py, tests/test_host_emul.py); the GPU tests still run on voxel_*.npz."""
+    vols = {}
+    rng = np.random.default_rng(7)
+    z, y, x = np.meshgrid(np.arange(7), np.arange(8), np.arange(7), indexing="ij")
+    blob = ((z - 3) ** 2 / 9.5 + (y - 3.5) ** 2 / 13 + (x - 3) ** 2 / 10) <= 1.0
+    # (f) kernelRadius 3 (343-voxel windows), 5 levels, ragged ROI
+    vols["r3"] = dict(image=rng.integers(1, 6, (7, 8, 7)).astype(np.int32), mask=blob & (rng.random(blob.shape) > 0.08),
+                      kw=dict(binWidth=1, kernelRadius=3))
+    # (g) the other weighting norms on anisotropic spacing
+    for norm in ("manhattan", "infinity", "no_weighting"):
+        vols[f"w_{norm}"] = dict(image=rng.integers(1, 6, (5, 6, 6)).astype(np.int32), mask=rng.random((5, 6, 6)) > 0.1,
+                                 spacing=(0.7, 1.3, 2.0), kw=dict(binWidth=1, weightingNorm=norm))
+    # (h) binCount on a float image
+    f = 300 * np.sin(z / 2.0) * np.cos(y / 3.0) + 40 * rng.normal(size=z.shape)
+    vols["bincount8"] = dict(image=f.astype(np.float64), mask=blob, kw=dict(binCount=8))
+    # (i) distance 2 only, kernelRadius 2
+    vols["d2_r2"] = dict(image=rng.integers(1, 7, (6, 6, 7)).astype(np.int32), mask=rng.random((6, 6, 7)) > 0.12,
+                         kw=dict(binWidth=1, kernelRadius=2, distances=[2]))
+    # (j) many levels (60) at kernelRadius 1: every window is all-distinct or nearly so
+    vols["ng60"] = dict(image=rng.integers(1, 61, (6, 7, 7)).astype(np.int32), mask=np.ones((6, 7, 7), bool), kw=dict(binWidth=1))
+    # (k) force2D along x, gldm_a = 2
+    vols["force2d_x_a2"] = dict(image=rng.integers(1, 7, (6, 7, 4)).astype(np.int32), mask=rng.random((6, 7, 4)) > 0.06,
+                                kw=dict(binWidth=1, force2D=True, force2Ddimension=2, gldm_a=2))
+    # (l) binWidth on negative intensities (lower bound below zero)
+    vols["negative"] = dict(image=(rng.integers(-260, 190, (6, 6, 6))).astype(np.int32), mask=rng.random((6, 6, 6)) > 0.1,
+                            kw=dict(binWidth=50))
+    return vols
+
+
+def voxel_goldens(extra=False):
+    for name, v in (voxel_volumes_extra() if extra else voxel_volumes()).items():
         sp = v.get("spacing", (1.0, 1.0, 1.0))
         out = {"image": v["image"], "mask": v["mask"], "spacing": np.array(sp),
                "settings": np.array(json.dumps(v["kw"]))}
@@ -130,7 +161,7 @@ def voxel_goldens():
                 logging.getLogger("radiomics").setLevel(logging.CRITICAL)
                 out["glcm_MCC_voxelBatch1"] = sitk.GetArrayFromImage(o1.execute()["MCC"])
                 logging.getLogger("radiomics").setLevel(logging.INFO)
-        np.savez_compressed(os.path.join(HERE, f"voxel_{name}.npz"), **out)
+        np.savez_compressed(os.path.join(HERE, f"voxel{'x' if extra else ''}_{name}.npz"), **out)
 
 
 def voxmat_goldens():
@@ -308,6 +339,9 @@ def resample_goldens():
 
 
 if __name__ == "__main__":
+    if "--voxel-extra-only" in sys.argv:
+        voxel_goldens(extra=True)
+        sys.exit(0)
     if "--resample-only" in sys.argv:
         resample_goldens()
         sys.exit(0)

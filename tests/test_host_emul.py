@@ -69,7 +69,7 @@ def test_feature_name_tables_match_library_order():
         assert len(names) == {"glcm": 24, "glrlm": 16, "glszm": 16, "gldm": 14, "ngtdm": 5}[cls]
 
 
-@pytest.mark.parametrize("name,z,kw", voxel_goldens(), ids=[g[0] for g in voxel_goldens()])
+@pytest.mark.parametrize("name,z,kw", voxel_goldens(extra=True), ids=[g[0] for g in voxel_goldens(extra=True)])
 def test_device_math_on_host_matches_reference_maps(emul, name, z, kw):
     lev, levels, Ng = binned(z, kw)
     lev16 = np.ascontiguousarray(lev, dtype=np.uint16)
@@ -110,21 +110,22 @@ def test_firstorder_device_math_on_host(emul, name, r):
             assert np.allclose(out[k][m], z[f"{name}_{f}"][m], rtol=1e-9, atol=1e-8), f
 
 
-@pytest.mark.parametrize("kind", ["uniform", "smooth"])
+@pytest.mark.parametrize("kind", ["uniform", "smooth", "uniform60"])
 def test_glcm_fast_math_equals_generic_math_on_host(emul, kind):
     """the r=1 GLCM fast path (sorting networks, bipartite filter, dense / Lanczos eigen-tasks) against the
     generic entry-list / Householder path on a 24^3 volume with holes -- catches solver regressions without a GPU."""
     rng = np.random.default_rng(2)
     shape = (24, 24, 24)
-    if kind == "uniform":
-        lev = rng.integers(1, 33, shape)
+    Ng = 60 if kind == "uniform60" else 32
+    if kind.startswith("uniform"):
+        lev = rng.integers(1, Ng + 1, shape)            # 60 levels: nearly every window is all-distinct (trees, n = 19)
     else:
         zz, yy, xx = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
         f = np.sin(zz / 2.7) + np.cos(yy / 3.1) + np.sin(xx / 2.3 + 1) + 0.25 * rng.normal(size=shape)
         lev = np.digitize(f, np.quantile(f, np.linspace(0, 1, 33)[1:-1])) + 1
         lev[5:9, 3:20, 7] = 0
     lev = np.ascontiguousarray(lev, dtype=np.uint16)
-    s = _lib.make_settings(32, 32)
+    s = _lib.make_settings(Ng, Ng)
     Zs, Ys, Xs = shape
     fast = np.zeros((24, Zs, Ys, Xs))
     gen = np.zeros((24, Zs, Ys, Xs))
@@ -331,15 +332,24 @@ def test_phaseA_graph_scan_against_bruteforce(emul):
     assert seen[(1, 1)] > 100 and seen[(1, 0)] > 500 and seen[(0, 0)] > 500, seen
 
 
-@pytest.mark.parametrize("kind", ["uniform", "smooth"])
+@pytest.mark.parametrize("kind", ["uniform", "smooth", "uniform200", "twolevel"])
 def test_glrlm_glszm_gldm_ngtdm_fast_math_equals_generic_math_on_host(emul, kind):
     """the r=1 bitmask fast paths (csrc/glrlm_fast.cuh, small_fast.cuh) against the generic entry-list kernels' math on a
     22^3 volume with holes (ragged windows, dropped GLRLM angles)"""
     rng = np.random.default_rng(3)
     shape = (22, 22, 22)
+    Ng = 32
     if kind == "uniform":
         lev = rng.integers(1, 33, shape)
         lev[rng.random(shape) < 0.1] = 0
+    elif kind == "uniform200":                        # every window all-singleton levels (the bulk path of GLRLM / GLSZM)
+        Ng = 200
+        lev = rng.integers(1, 201, shape)
+        lev[rng.random(shape) < 0.05] = 0
+    elif kind == "twolevel":                          # no singleton at all: two levels in big zones / long runs, sparse holes
+        zz, yy, xx = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
+        lev = 1 + ((zz // 3 + yy // 2 + xx // 4) % 2) * 6
+        lev[rng.random(shape) < 0.03] = 0
     else:
         zz, yy, xx = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
         f = np.sin(zz / 2.7) + np.cos(yy / 3.1) + np.sin(xx / 2.3 + 1) + 0.25 * rng.normal(size=shape)
@@ -347,7 +357,7 @@ def test_glrlm_glszm_gldm_ngtdm_fast_math_equals_generic_math_on_host(emul, kind
         lev[5:9, 3:20, 7] = 0
         lev[12, :, :] = 0                         # a plane of holes: windows that lose whole GLRLM angles
     lev = np.ascontiguousarray(lev, dtype=np.uint16)
-    s = _lib.make_settings(32, 32)
+    s = _lib.make_settings(Ng, Ng)
     Zs, Ys, Xs = shape
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     for cid, cname in enumerate(_lib.CLASSES):

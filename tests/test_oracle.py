@@ -120,7 +120,7 @@ def test_pipeline_reproduces_reference_feature_baseline(seg, cname):
             assert abs(got[f] - v) <= 1e-9 * max(abs(v), 1e-12), (cname, test, f, got[f], v)
 
 
-@pytest.mark.parametrize("name,z,kw", voxel_goldens(), ids=[g[0] for g in voxel_goldens()])
+@pytest.mark.parametrize("name,z,kw", voxel_goldens(extra=True), ids=[g[0] for g in voxel_goldens(extra=True)])
 def test_pipeline_reproduces_reference_voxel_maps(name, z, kw):
     m = z["mask"]
     for cname in PL.CLASS_NAMES:
