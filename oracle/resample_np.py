@@ -13,16 +13,19 @@ from __future__ import annotations
 import numpy as np
 
 
-def grid(mask, spacing_xyz, new_spacing_xyz, padDistance=5, label=1):
-    """(newSize xyz, start xyz, step xyz, newSpacing): output voxel k samples the input at continuous index start + k*step"""
+def grid(mask, spacing_xyz, new_spacing_xyz, padDistance=5, label=1, offset_xyz=(0, 0, 0), full_size_xyz=None):
+    """(newSize xyz, start xyz, step xyz, newSpacing): output voxel k samples the input at continuous index start + k*step.
+    `offset_xyz` / `full_size_xyz`: the arrays are a crop of a larger image starting at that index -- the output grid is
+    anchored at the FULL image's index 0 (imageoperations.py:520-548), so a committed crop must say where it sat."""
     sp = np.array(spacing_xyz, float)
     new = np.array(new_spacing_xyz, float)
     new = np.where(new == 0, sp, new)
     idx = np.array(np.where(np.asarray(mask) == label))
     lo, hi = idx.min(1)[::-1], idx.max(1)[::-1]
-    bb = np.concatenate([lo, hi - lo + 1]).astype(float)
+    off = np.array(offset_xyz, float)
+    bb = np.concatenate([lo + off, hi - lo + 1]).astype(float)
     nd = len(sp)
-    size = np.array(np.asarray(mask).shape[::-1], float)
+    size = np.array(np.asarray(mask).shape[::-1] if full_size_xyz is None else full_size_xyz, float)
     new = np.where(bb[nd:] != 1, new, sp)
     ratio = sp / new
     L = np.floor((bb[:nd] - 0.5) * ratio - padDistance)
@@ -30,13 +33,13 @@ def grid(mask, spacing_xyz, new_spacing_xyz, padDistance=5, label=1):
     maxU = np.ceil(size * ratio) - 1
     L = np.where(L < 0, 0, L)
     U = np.where(U > maxU, maxU, U)
-    return (U - L + 1).astype(int), 0.5 * (new - sp) / sp + L / ratio, new / sp, new
+    return (U - L + 1).astype(int), 0.5 * (new - sp) / sp + L / ratio - off, new / sp, new
 
 
-def resample(image, mask, spacing_xyz, new_spacing_xyz, padDistance=5, label=1, order=3):
+def resample(image, mask, spacing_xyz, new_spacing_xyz, padDistance=5, label=1, order=3, offset_xyz=(0, 0, 0), full_size_xyz=None):
     import scipy.ndimage as ndi
     image, mask = np.asarray(image), np.asarray(mask)
-    newSize, start, step, new = grid(mask, spacing_xyz, new_spacing_xyz, padDistance, label)
+    newSize, start, step, new = grid(mask, spacing_xyz, new_spacing_xyz, padDistance, label, offset_xyz, full_size_xyz)
     g = [start[d] + step[d] * np.arange(newSize[d]) for d in range(3)]          # x, y, z
     zz, yy, xx = np.meshgrid(g[2], g[1], g[0], indexing="ij")
     if order == 3:

@@ -336,6 +336,37 @@ def resample_goldens():
     np.savez_compressed(os.path.join(HERE, "resample_breast1.npz"), image=img, mask=msk.astype(np.uint8), spacing=np.array(sp),
                         names=np.array(sorted(exp)), values=np.array([exp[k] for k in sorted(exp)]))
     print("resample golden", img.shape, sp, len(exp), "values")
+    # the other four bundled cases, cropped: ROI box + the pad distance + 16 voxels (the cubic B-spline decomposition forgets
+    # a mirrored edge after ~16 samples), with the index the crop started at and the full size -- the output grid is
+    # anchored at the full image's index 0.  The crop resamples to exactly the arrays of the whole image (checked here).
+    import resample_np as RS
+    out = {}
+    for case in ("brain1", "brain2", "lung1", "lung2"):
+        img, sp = rh.read_nrrd(os.path.join(rh.REF_ROOT, "data", f"{case}_image.nrrd"))
+        msk, _ = rh.read_nrrd(os.path.join(rh.REF_ROOT, "data", f"{case}_label.nrrd"))
+        msk = msk.astype(np.uint8)
+        exp = {}
+        for cls in ("firstorder", "glcm", "glrlm", "glszm", "gldm", "ngtdm", "shape"):
+            rows = list(csv.reader(open(os.path.join(rh.REF_ROOT, "data", "baseline", f"baseline_{cls}.csv"))))
+            i = rows[0].index(f"{case}_resampling")
+            for r in rows[1:]:
+                if r[0].startswith("original_"):
+                    exp[r[0]] = float(r[i])
+        idx = np.array(np.where(msk == 1))
+        marg = np.ceil((5 * 2.0 + 2.0) / np.array(sp)[::-1]).astype(int) + 16
+        a = np.maximum(idx.min(1) - marg, 0)
+        b = np.minimum(idx.max(1) + marg + 1, np.array(img.shape))
+        sl = tuple(slice(x, y) for x, y in zip(a, b))
+        ci, cm = np.ascontiguousarray(img[sl]), np.ascontiguousarray(msk[sl])
+        off, full = tuple(int(v) for v in a[::-1]), img.shape[::-1]
+        whole = RS.resample(img, msk, sp, (2, 2, 2))
+        crop = RS.resample(ci, cm, sp, (2, 2, 2), offset_xyz=off, full_size_xyz=full)
+        assert np.array_equal(whole[0], crop[0]) and np.array_equal(whole[1], crop[1]), case
+        out.update({f"{case}_image": ci, f"{case}_mask": cm, f"{case}_spacing": np.array(sp), f"{case}_offset_xyz": np.array(off),
+                    f"{case}_full_size_xyz": np.array(full), f"{case}_names": np.array(sorted(exp)),
+                    f"{case}_values": np.array([exp[k] for k in sorted(exp)])})
+        print("resample golden", case, ci.shape, "of", img.shape, len(exp), "values")
+    np.savez_compressed(os.path.join(HERE, "resample_cases.npz"), **out)
 
 
 if __name__ == "__main__":

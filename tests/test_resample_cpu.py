@@ -5,6 +5,7 @@ the `breast1_resampling` column of data/baseline/baseline_{firstorder,glcm,glrlm
 import os
 
 import numpy as np
+import pytest
 
 import firstorder_np as FO
 import pipeline as PL
@@ -37,6 +38,21 @@ def test_oracle_resampling_reproduces_the_reference_baseline_column():
         assert np.isclose(got[k], exp[k], rtol=1e-9, atol=1e-12), (k, got[k], exp[k])
     # the cast is a truncation: rounding to nearest changes the ROI mean (126.87 instead of the baseline's 126.17)
     assert exp["original_firstorder_Mean"] == 126.17391304347827
+
+
+@pytest.mark.parametrize("case", ["brain1", "brain2", "lung1", "lung2"])
+def test_oracle_resampling_reproduces_the_other_four_baseline_columns(case):
+    """`<case>_resampling` of the seven baseline CSVs for the other bundled cases (tests/golden/resample_cases.npz: the ROI
+    box + pad + 16 voxels of each image, with the index the crop started at -- it resamples to exactly the whole image's arrays)"""
+    z = np.load(os.path.join(G, "resample_cases.npz"))
+    exp = dict(zip(z[case + "_names"], z[case + "_values"]))
+    img, msk, new = RS.resample(z[case + "_image"], z[case + "_mask"], z[case + "_spacing"], (2, 2, 2),
+                                offset_xyz=tuple(z[case + "_offset_xyz"]), full_size_xyz=tuple(z[case + "_full_size_xyz"]))
+    got = _features(img, msk, new)
+    hit = [k for k in exp if k in got]
+    assert len(hit) == 107
+    for k in hit:
+        assert np.isclose(got[k], exp[k], rtol=1e-9, atol=1e-12), (case, k, got[k], exp[k])
 
 
 def test_grid_arithmetic_special_cases():
