@@ -78,6 +78,57 @@ def segment_goldens():
     json.dump(expect, open(os.path.join(HERE, "segment_expect.json"), "w"), indent=0, sort_keys=True)
 
 
+def segment_goldens_resegmented():
+    """the `_flatRegion` (resegmentRange [0], binWidth 5000: one gray level) and `_resegmentation` (sigma mode, [-3, 3])
+    columns of the five texture baselines.  The mask is resegmented by the REFERENCE's own imageoperations.resegmentMask
+    (plain NumPy, runs through the harness) on the ROI crop; mask + expected values -> segment_extra.npz / segment_expect_extra.json
+    (oracle pins on the CPU box; the flat region is the single-level edge case of getBinEdges and of every class)."""
+    from radiomics import imageoperations as rio
+    arrays, expect = {}, {}
+    for cname, cls in CLASSES.items():
+        rows = list(csv.reader(open(os.path.join(rh.REF_ROOT, "data", "baseline", f"baseline_{cname}.csv"))))
+        header = rows[0]
+        byname = {r[0]: r for r in rows}
+        for col in range(1, len(header)):
+            test = header[col]
+            if not (test.endswith("_flatRegion") or test.endswith("_resegmentation") or test.endswith("_normalization")):
+                continue
+            case = byname["diagnostics_Configuration_TestCase"][col]
+            settings = ast.literal_eval(byname["diagnostics_Configuration_Settings"][col])
+            assert not settings.get("resampledPixelSpacing")
+            kw = {k: v for k, v in settings.items() if k in HOT_KEYS and v is not None}
+            img, m, sp = rh.load_case(case)
+            if test.endswith("_normalization"):
+                # normalizeImage (imageoperations.py:615-654) = sitk.Normalize over the WHOLE image, times normalizeScale.
+                # SimpleITK is absent: restated as (x - mean) / std (N-1), checked against the baseline through the
+                # reference's own feature class below; mean / std of the whole image travel with the fixture
+                full, _ = rh.read_nrrd(os.path.join(rh.REF_ROOT, "data", f"{case}_image.nrrd"))
+                mu, sd = float(full.astype(np.float64).mean()), float(full.astype(np.float64).std(ddof=1))
+                scale = float(settings.get("normalizeScale", 1))
+                nimg = (img.astype(np.float64) - mu) / sd * scale
+                feats = {r[0].split("_", 2)[2]: float(r[col]) for r in rows if r[0].startswith(f"original_{cname}_")}
+                got = cls(sitk.Image(nimg, sp), sitk.Image(m.astype(np.uint8), sp), **kw).execute()
+                worst = max(abs(float(got[f]) - v) / max(abs(v), 1e-300) for f, v in feats.items())
+                assert worst < 1e-9, (cname, test, worst)
+                expect.setdefault(cname, {})[test] = {"case": case, "settings": kw, "features": feats,
+                                                      "normalize": {"mean": mu, "std": sd, "scale": scale}}
+                print("segment extra", cname, test, "normalised, ok rel", worst)
+                continue
+            im_s, ma_s = sitk.Image(img, sp), sitk.Image(m.astype(np.uint8), sp)
+            ma_r = rio.resegmentMask(im_s, ma_s, resegmentRange=settings["resegmentRange"],
+                                     resegmentMode=settings.get("resegmentMode", "absolute"), label=1)
+            mr = sitk.GetArrayFromImage(ma_r) == 1
+            feats = {r[0].split("_", 2)[2]: float(r[col]) for r in rows if r[0].startswith(f"original_{cname}_")}
+            got = cls(im_s, sitk.Image(mr.astype(np.uint8), sp), **kw).execute()
+            worst = max(abs(float(got[f]) - v) / max(abs(v), 1e-300) for f, v in feats.items())
+            assert worst < 1e-9, (cname, test, worst)
+            arrays[f"{test}_mask"] = mr
+            expect.setdefault(cname, {})[test] = {"case": case, "settings": kw, "features": feats}
+            print("segment extra", cname, test, "roi", int(mr.sum()), "of", int(m.sum()), "ok rel", worst)
+    np.savez_compressed(os.path.join(HERE, "segment_extra.npz"), **arrays)
+    json.dump(expect, open(os.path.join(HERE, "segment_expect_extra.json"), "w"), indent=0, sort_keys=True)
+
+
 def voxel_volumes():
     vols = {}
     rng = np.random.default_rng(0)
@@ -370,6 +421,9 @@ def resample_goldens():
 
 
 if __name__ == "__main__":
+    if "--segment-extra-only" in sys.argv:
+        segment_goldens_resegmented()
+        sys.exit(0)
     if "--voxel-extra-only" in sys.argv:
         voxel_goldens(extra=True)
         sys.exit(0)

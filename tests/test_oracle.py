@@ -120,6 +120,27 @@ def test_pipeline_reproduces_reference_feature_baseline(seg, cname):
             assert abs(got[f] - v) <= 1e-9 * max(abs(v), 1e-12), (cname, test, f, got[f], v)
 
 
+@pytest.mark.parametrize("cname", PL.CLASS_NAMES)
+def test_pipeline_reproduces_the_resegmented_baseline_columns(seg, cname):
+    """`<case>_flatRegion` (one gray level: the single-edge branch of getBinEdges, every class on a flat ROI),
+    `<case>_resegmentation` (masks resegmented by the reference's own resegmentMask) and `<case>_normalization` (float image,
+    binWidth 5) columns (tests/golden/make_golden.py --segment-extra-only): with these and the resampling columns
+    (test_resample_cpu.py) the oracle reproduces ALL 40 columns of each texture baseline CSV"""
+    cases, _ = seg
+    masks = np.load(os.path.join(GOLDEN, "segment_extra.npz"))
+    expect = json.load(open(os.path.join(GOLDEN, "segment_expect_extra.json")))
+    assert len(expect[cname]) == 15
+    for test, e in expect[cname].items():
+        c = e["case"]
+        img, m = cases[c + "_image"], (masks[test + "_mask"] if test + "_mask" in masks.files else cases[c + "_mask"])
+        if "normalize" in e:                 # `<case>_normalization`: (x - mean) / std of the WHOLE image, times normalizeScale
+            n = e["normalize"]
+            img = (img.astype(np.float64) - n["mean"]) / n["std"] * n["scale"]
+        got = PL.extract(cname, img, m, spacing_zyx=cases[c + "_spacing"][::-1], **e["settings"])
+        for f, v in e["features"].items():
+            assert abs(got[f] - v) <= 1e-9 * max(abs(v), 1e-12), (cname, test, f, got[f], v)
+
+
 @pytest.mark.parametrize("name,z,kw", voxel_goldens(extra=True), ids=[g[0] for g in voxel_goldens(extra=True)])
 def test_pipeline_reproduces_reference_voxel_maps(name, z, kw):
     m = z["mask"]
