@@ -83,9 +83,9 @@ def segment_goldens_resegmented():
     columns of the five texture baselines.  The mask is resegmented by the REFERENCE's own imageoperations.resegmentMask
     (plain NumPy, runs through the harness) on the ROI crop; mask + expected values -> segment_extra.npz / segment_expect_extra.json
     (oracle pins on the CPU box; the flat region is the single-level edge case of getBinEdges and of every class)."""
-    from radiomics import imageoperations as rio
+    from radiomics import firstorder, imageoperations as rio
     arrays, expect = {}, {}
-    for cname, cls in CLASSES.items():
+    for cname, cls in list(CLASSES.items()) + [("firstorder", firstorder.RadiomicsFirstOrder)]:
         rows = list(csv.reader(open(os.path.join(rh.REF_ROOT, "data", "baseline", f"baseline_{cname}.csv"))))
         header = rows[0]
         byname = {r[0]: r for r in rows}
@@ -96,7 +96,7 @@ def segment_goldens_resegmented():
             case = byname["diagnostics_Configuration_TestCase"][col]
             settings = ast.literal_eval(byname["diagnostics_Configuration_Settings"][col])
             assert not settings.get("resampledPixelSpacing")
-            kw = {k: v for k, v in settings.items() if k in HOT_KEYS and v is not None}
+            kw = {k: v for k, v in settings.items() if k in HOT_KEYS | {"voxelArrayShift"} and v is not None}
             img, m, sp = rh.load_case(case)
             if test.endswith("_normalization"):
                 # normalizeImage (imageoperations.py:615-654) = sitk.Normalize over the WHOLE image, times normalizeScale.

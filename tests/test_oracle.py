@@ -150,6 +150,25 @@ def test_pipeline_reproduces_reference_voxel_maps(name, z, kw):
             assert_maps_close(arr, ref_map(z, cname, f)[m], f"{name}/{cname}/{f}", rtol=1e-8, atol=1e-10)
 
 
+def test_firstorder_oracle_reproduces_the_resegmented_and_normalised_columns(seg):
+    """`<case>_resegmentation` / `<case>_normalization` of baseline_firstorder.csv (with the base and the resampling columns:
+    all 20)"""
+    import firstorder_np as FO
+    cases, _ = seg
+    masks = np.load(os.path.join(GOLDEN, "segment_extra.npz"))
+    expect = json.load(open(os.path.join(GOLDEN, "segment_expect_extra.json")))["firstorder"]
+    assert len(expect) == 10
+    for test, e in expect.items():
+        c = e["case"]
+        img, m = cases[c + "_image"], (masks[test + "_mask"] if test + "_mask" in masks.files else cases[c + "_mask"])
+        if "normalize" in e:
+            n = e["normalize"]
+            img = (img.astype(np.float64) - n["mean"]) / n["std"] * n["scale"]
+        got = FO.extract(img, m, spacing_xyz=cases[c + "_spacing"], **e["settings"])
+        for f, v in e["features"].items():
+            assert abs(got[f] - v) <= 1e-9 * max(abs(v), 1e-12), (test, f, got[f], v)
+
+
 def test_firstorder_oracle_reproduces_reference():
     """oracle/firstorder_np.py against data/baseline/baseline_firstorder.csv and the reference's voxel run"""
     import firstorder_np as FO
