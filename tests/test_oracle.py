@@ -125,7 +125,7 @@ def test_pipeline_reproduces_the_resegmented_baseline_columns(seg, cname):
     """`<case>_flatRegion` (one gray level: the single-edge branch of getBinEdges, every class on a flat ROI),
     `<case>_resegmentation` (masks resegmented by the reference's own resegmentMask) and `<case>_normalization` (float image,
     binWidth 5) columns (tests/golden/make_golden.py --segment-extra-only): with these and the resampling columns
-    (test_resample_cpu.py) the oracle reproduces ALL 40 columns of each texture baseline CSV"""
+    (test_resample_cpu.py) the oracle reproduces EVERY column of the five texture baseline CSVs (185)"""
     cases, _ = seg
     masks = np.load(os.path.join(GOLDEN, "segment_extra.npz"))
     expect = json.load(open(os.path.join(GOLDEN, "segment_expect_extra.json")))

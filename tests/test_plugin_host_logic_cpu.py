@@ -1,0 +1,126 @@
+"""The PRODUCT's plugin classes on the CPU box: everything above the device layer -- matrix post-processing
+(symmetrise / weight / empty-angle drop), the scalar feature formulas of pyradiomics_b200/_matrix_features.py, feature
+enabling, deprecated features -- runs unchanged; only the three calls that need a GPU (the per-image discretisation and the
+two device matrix builders) are replaced, in this test, by the oracle's C port of the reference.  Checked against EVERY
+column of the reference's five texture baseline CSVs that does not need resampling (160 of 185) and against the
+reference's golden matrices.  (The same classes over the CUDA matrices: tests/test_plugins_gpu.py.)"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cmatrices_oracle as O
+import pipeline as PL
+from helpers import GOLDEN
+from pyradiomics_b200 import cmatrices, featureclasses as FC, image as I
+
+CLASSES = ("glcm", "glrlm", "glszm", "gldm", "ngtdm")
+
+
+class OracleDeviceImage:
+    """stands in for featureclasses.DeviceImage: numpy binning + the oracle's matrices (test only)"""
+
+    def __init__(self, imageArray, maskRaw, label, masked, settings):
+        m = np.asarray(maskRaw) == label
+        lev, self.edges, levels, Ng = PL.bin_image(np.asarray(imageArray), m, settings.get("binWidth", 25), settings.get("binCount"))
+        self.lev = np.ascontiguousarray(np.where(m, lev, 0), dtype=np.int32)
+        self.mask = m
+        self.grayLevels = np.asarray(levels, np.int64)
+        self.Ng = int(Ng)
+        self.levels = self                      # the "device tensor" handed to cmatrices.calculate_*_device below
+
+    def binned_host(self):
+        return self.lev.astype(np.int64)
+
+    def segment_texture(self, distances, alpha, force2D, force2Ddimension):
+        d = np.array(list(distances), np.int32)
+        f2d = force2Ddimension if force2D else -1
+        Pg, ang = O.calculate_glcm(self.lev, self.mask, d, self.Ng, force2D, f2d)
+        return {"glcm": (Pg, ang), "gldm": O.calculate_gldm(self.lev, self.mask, d, self.Ng, int(alpha), force2D, f2d),
+                "ngtdm": O.calculate_ngtdm(self.lev, self.mask, d, self.Ng, force2D, f2d)}
+
+
+@pytest.fixture()
+def oracle_device(monkeypatch):
+    monkeypatch.setattr(FC, "device_image", lambda img, msk, label, masked, settings: OracleDeviceImage(img, msk, label, masked, settings))
+    monkeypatch.setattr(cmatrices, "calculate_glrlm_device",
+                        lambda dev, Ng, Nr, f2, f2d: O.calculate_glrlm(dev.lev, dev.mask, Ng, Nr, f2, f2d if f2 else -1))
+    monkeypatch.setattr(cmatrices, "calculate_glszm_device",
+                        lambda dev, Ng, f2, f2d: O.calculate_glszm(dev.lev, dev.mask, Ng, int(dev.mask.sum()), f2, f2d if f2 else -1))
+
+
+def _columns():
+    cases = np.load(os.path.join(GOLDEN, "segment_cases.npz"))
+    base = json.load(open(os.path.join(GOLDEN, "segment_expect.json")))
+    extra = json.load(open(os.path.join(GOLDEN, "segment_expect_extra.json")))
+    masks = np.load(os.path.join(GOLDEN, "segment_extra.npz"))
+    return cases, base, extra, masks
+
+
+@pytest.mark.parametrize("cname", CLASSES)
+def test_plugin_classes_over_oracle_matrices_match_every_baseline_column(oracle_device, cname):
+    cases, base, extra, masks = _columns()
+    cols = dict(base[cname])
+    cols.update(extra[cname])
+    assert len(cols) == (35 if cname in ("glcm", "glrlm") else 30)      # (the *_combined columns exist for GLCM / GLRLM only)
+    for test, e in cols.items():
+        c = e["case"]
+        img = cases[c + "_image"]
+        m = masks[test + "_mask"] if test + "_mask" in masks.files else cases[c + "_mask"]
+        if "normalize" in e:
+            n = e["normalize"]
+            img = (img.astype(np.float64) - n["mean"]) / n["std"] * n["scale"]
+        obj = FC.FEATURE_CLASSES[cname](I.ArrayImage(img, cases[c + "_spacing"]), I.ArrayImage(m.astype(np.uint8), cases[c + "_spacing"]),
+                                        **e["settings"])
+        got = obj.execute()
+        assert set(got) == set(e["features"]), (test, set(got) ^ set(e["features"]))
+        for f, v in e["features"].items():
+            assert abs(float(got[f]) - v) <= 1e-9 * max(abs(v), 1e-12), (cname, test, f, float(got[f]), v)
+
+
+@pytest.mark.parametrize("case", ["brain1", "brain2", "breast1", "lung1", "lung2"])
+def test_plugin_processed_matrices_over_oracle_matrices_match_the_golden_matrices(oracle_device, case):
+    """reference tests/test_matrices.py:35-65 through the product's _calculateMatrix post-processing"""
+    cases = np.load(os.path.join(GOLDEN, "segment_cases.npz"))
+    img = I.ArrayImage(cases[case + "_image"], cases[case + "_spacing"])
+    msk = I.ArrayImage(cases[case + "_mask"].astype(np.uint8), cases[case + "_spacing"])
+    for cname in CLASSES:
+        obj = FC.FEATURE_CLASSES[cname](img, msk, binWidth=25)
+        obj._initCalculation()
+        P = getattr(obj, "P_" + cname)[0]
+        assert P.shape == cases[f"{case}_{cname}_P"].shape
+        assert np.abs(P - cases[f"{case}_{cname}_P"]).max() < 1e-12
+
+
+def test_plugin_feature_enabling_and_deprecated_features(oracle_device):
+    cases = np.load(os.path.join(GOLDEN, "segment_cases.npz"))
+    img, msk = cases["breast1_image"], cases["breast1_mask"].astype(np.uint8)
+    obj = FC.RadiomicsGLCM(img, msk, binWidth=25)
+    obj.enableFeatureByName("Contrast")
+    obj.enableFeatureByName("Homogeneity1")          # deprecated in the reference: enabled by name -> skipped, not an error
+    got = obj.execute()
+    assert set(got) == {"Contrast"}
+    with pytest.raises(LookupError):
+        obj.enableFeatureByName("NoSuchFeature")
+    assert FC.RadiomicsGLCM.getFeatureNames()["Homogeneity1"] is True and FC.RadiomicsGLCM.getFeatureNames()["Contrast"] is False
+
+
+def test_plugin_firstorder_segment_mode_matches_every_baseline_column_without_resampling(oracle_device):
+    """RadiomicsFirstOrder reduces the ROI vector on the host in segment mode: base, resegmentation and normalization columns
+    of baseline_firstorder.csv (15 of 20; the resampling ones need the GPU resampler, tests/test_resample_gpu.py)"""
+    cases, _, extra, masks = _columns()
+    cols = dict(json.load(open(os.path.join(GOLDEN, "segment_expect_firstorder.json"))))
+    cols.update(extra["firstorder"])
+    assert len(cols) == 15
+    for test, e in cols.items():
+        c = e["case"]
+        img = cases[c + "_image"]
+        m = masks[test + "_mask"] if test + "_mask" in masks.files else cases[c + "_mask"]
+        if "normalize" in e:
+            n = e["normalize"]
+            img = (img.astype(np.float64) - n["mean"]) / n["std"] * n["scale"]
+        sp = cases[c + "_spacing"]
+        got = FC.RadiomicsFirstOrder(I.ArrayImage(img, sp), I.ArrayImage(m.astype(np.uint8), sp), **e["settings"]).execute()
+        for f, v in e["features"].items():
+            assert abs(float(got[f]) - v) <= 1e-9 * max(abs(v), 1e-12), (test, f, float(got[f]), v)
