@@ -124,3 +124,64 @@ def test_plugin_firstorder_segment_mode_matches_every_baseline_column_without_re
         got = FC.RadiomicsFirstOrder(I.ArrayImage(img, sp), I.ArrayImage(m.astype(np.uint8), sp), **e["settings"]).execute()
         for f, v in e["features"].items():
             assert abs(float(got[f]) - v) <= 1e-9 * max(abs(v), 1e-12), (test, f, float(got[f]), v)
+
+
+# ---- shape classes: the formulas above the device coefficients (reference shape.py / shape2D.py)
+@pytest.fixture()
+def oracle_shape(monkeypatch):
+    import shape_np as S
+    from pyradiomics_b200 import cshape, imageoperations as IO
+    monkeypatch.setattr(IO, "_to_device", lambda a: np.asarray(a))
+
+    def coeff(mask, spacing_zyx):
+        sa, vol, dia = S.coefficients(np.asarray(mask), np.asarray(spacing_zyx))
+        return sa, vol, list(dia), 0
+
+    def moments(mask):
+        z, y, x = [c.astype(object) for c in np.nonzero(np.asarray(mask))]       # Python ints: exact like the kernel's 64-bit sums
+        return [len(z), int(z.sum()), int(y.sum()), int(x.sum()), int((z * z).sum()), int((z * y).sum()), int((z * x).sum()),
+                int((y * y).sum()), int((y * x).sum()), int((x * x).sum())]
+
+    monkeypatch.setattr(cshape, "coefficients_device", coeff)
+    monkeypatch.setattr(cshape, "moments_device", moments)
+    monkeypatch.setattr(cshape, "calculate_coefficients2D", lambda m, sp: S.coefficients2d(np.asarray(m), np.asarray(sp)))
+
+
+@pytest.mark.parametrize("case", ["brain1", "brain2", "breast1", "lung1", "lung2"])
+def test_plugin_shape_class_over_oracle_coefficients(oracle_shape, case):
+    """RadiomicsShape's formulas (sphericity, axis lengths from exact integer moments, ...) against the reference class's own
+    values (tests/golden/shape_expect.json: full precision) and the baseline CSV"""
+    exp = json.load(open(os.path.join(GOLDEN, "shape_expect.json")))[case]
+    seg = np.load(os.path.join(GOLDEN, "segment_cases.npz"))
+    sp = seg[case + "_spacing"]
+    obj = FC.RadiomicsShape(I.ArrayImage(seg[case + "_image"], sp), I.ArrayImage(seg[case + "_mask"].astype(np.uint8), sp))
+    got = obj.execute()
+    assert set(got) == set(FC.RadiomicsShape.NAMES)
+    for f, v in exp["features"].items():
+        if f in got:
+            assert float(got[f]) == pytest.approx(v, rel=1e-9), f
+    for f, v in exp["baseline"].items():
+        assert float(got[f]) == pytest.approx(v, rel=0.03), f
+
+
+def test_plugin_shape2d_class_over_oracle_coefficients(oracle_shape):
+    import shape_np as S
+    d = np.load(os.path.join(GOLDEN, "shape2d_golden.npz"))
+    for name in ("disc", "noise", "ring"):
+        m, sp = d[name + "_mask"], d[name + "_spacing"]
+        ref = S.features2d(m, sp)
+        obj = FC.RadiomicsShape2D(I.ArrayImage(m.astype(np.float64), tuple(sp[::-1])), I.ArrayImage(m.astype(np.uint8), tuple(sp[::-1])))
+        got = obj.execute()
+        assert set(got) == set(FC.RadiomicsShape2D.NAMES)
+        for f in got:
+            assert float(got[f]) == pytest.approx(ref[f], rel=1e-10, nan_ok=True), (name, f)
+    # a 3-D mask with one slice + force2D (shape2D.py:62-84); more than one slice is refused
+    m, sp = d["disc_mask"], d["disc_spacing"]
+    m3 = m[None]
+    obj = FC.RadiomicsShape2D(I.ArrayImage(m3.astype(np.float64), (sp[1], sp[0], 3.0)), I.ArrayImage(m3.astype(np.uint8), (sp[1], sp[0], 3.0)),
+                              force2D=True, force2Ddimension=0)
+    ref = S.features2d(m, sp)
+    got = obj.execute()
+    assert float(got["Perimeter"]) == pytest.approx(ref["Perimeter"], rel=1e-12)
+    with pytest.raises(ValueError):
+        FC.RadiomicsShape2D(np.zeros((2,) + m.shape), np.repeat(m3, 2, 0).astype(np.uint8), force2D=True, force2Ddimension=0).execute()
