@@ -185,3 +185,86 @@ def test_plugin_shape2d_class_over_oracle_coefficients(oracle_shape):
     assert float(got["Perimeter"]) == pytest.approx(ref["Perimeter"], rel=1e-12)
     with pytest.raises(ValueError):
         FC.RadiomicsShape2D(np.zeros((2,) + m.shape), np.repeat(m3, 2, 0).astype(np.uint8), force2D=True, force2Ddimension=0).execute()
+
+
+# ---- resampleImage: the geometry arithmetic of the product (grid anchored at index 0, pad, clipping, single-slice rule,
+# origin of the new grid) with the GPU interpolation replaced by scipy's (test only)
+@pytest.fixture()
+def scipy_resampler(monkeypatch):
+    import scipy.ndimage as ndi
+    import torch
+    from pyradiomics_b200 import imageoperations as IO
+
+    def to_dev(a):
+        a = np.ascontiguousarray(np.asarray(a))
+        return torch.from_numpy(a.view(np.uint8) if a.dtype == np.bool_ else a)
+
+    def resample_device(arr_t, out_size_zyx, start_zyx, step_zyx, interpolator=3, default_value=0.0, out_dtype=None):
+        a = arr_t.numpy()
+        g = [start_zyx[d] + step_zyx[d] * np.arange(out_size_zyx[d]) for d in range(3)]
+        zz, yy, xx = np.meshgrid(*g, indexing="ij")
+        if interpolator == 3:
+            coef = ndi.spline_filter(a.astype(np.float64), order=3, mode="mirror") if min(a.shape) > 1 else None
+            if coef is None:                                   # a singleton axis: filter the others only
+                coef = a.astype(np.float64)
+                for ax in range(3):
+                    if a.shape[ax] > 1:
+                        coef = ndi.spline_filter1d(coef, order=3, axis=ax, mode="mirror")
+            val = ndi.map_coordinates(coef, [zz, yy, xx], order=3, mode="mirror", prefilter=False)
+        elif interpolator == 1:
+            val = ndi.map_coordinates(a.astype(np.float64), [zz, yy, xx], order=1, mode="nearest")
+        else:
+            val = ndi.map_coordinates(a.astype(np.float64), [np.floor(zz + 0.5), np.floor(yy + 0.5), np.floor(xx + 0.5)], order=0, mode="nearest")
+        inside = np.ones(val.shape, bool)
+        for c, n in ((zz, a.shape[0]), (yy, a.shape[1]), (xx, a.shape[2])):
+            inside &= (c >= -0.5) & (c < n - 0.5)
+        val = np.where(inside, val, default_value)
+        if np.issubdtype(a.dtype, np.integer):
+            info = np.iinfo(a.dtype)
+            val = np.trunc(np.clip(val, info.min, info.max))
+        return torch.from_numpy(np.ascontiguousarray(val.astype(a.dtype)))
+
+    monkeypatch.setattr(IO, "_to_device", to_dev)
+    monkeypatch.setattr(IO, "resample_device", resample_device)
+    return IO
+
+
+def test_plugin_resampleImage_grid_equals_the_oracle_on_the_baseline_case(scipy_resampler):
+    import resample_np as RS
+    IO = scipy_resampler
+    z = np.load(os.path.join(GOLDEN, "resample_breast1.npz"))
+    sp = tuple(float(v) for v in z["spacing"])
+    for new, interp in (((2, 2, 2), "sitkBSpline"), ((1.5, 1.0, 0), "sitkBSpline"), ((3, 3, 3), "sitkLinear"), ((2, 2, 2), "sitkNearestNeighbor")):
+        ri, rm = IO.resampleImage(I.ArrayImage(z["image"], sp), I.ArrayImage(z["mask"], sp), resampledPixelSpacing=list(new),
+                                  interpolator=interp, padDistance=5)
+        order = {"sitkBSpline": 3, "sitkLinear": 1, "sitkNearestNeighbor": 0}[interp]
+        oi, om, onew = RS.resample(z["image"], z["mask"], sp, new, order=order)
+        assert np.array_equal(I.as_array(rm), om), (new, interp)
+        if order != 0:
+            assert np.array_equal(I.as_array(ri), oi), (new, interp)
+        assert np.allclose(I.spacing_xyz(ri), onew) and I.as_array(ri).dtype == z["image"].dtype
+        size, start, step, _ = RS.grid(z["mask"], sp, new)
+        assert np.allclose(I.origin_xyz(ri), np.array(start) * np.array(sp))        # TransformContinuousIndexToPhysicalPoint of voxel 0
+    # same spacing: nothing to interpolate, the call degenerates to the crop (:517-537)
+    ci, cm = IO.resampleImage(I.ArrayImage(z["image"], sp), I.ArrayImage(z["mask"], sp), resampledPixelSpacing=list(sp), padDistance=2)
+    idx = np.array(np.where(z["mask"] == 1))
+    want = tuple(slice(max(int(a) - 2, 0), min(int(b) + 3, n)) for a, b, n in zip(idx.min(1), idx.max(1), z["mask"].shape))
+    assert np.array_equal(I.as_array(cm), z["mask"][want]) and np.array_equal(I.as_array(ci), z["image"][want])
+
+
+def test_plugin_resampleImage_single_slice_roi_and_errors(scipy_resampler):
+    import resample_np as RS
+    IO = scipy_resampler
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 500, (6, 20, 22)).astype(np.int16)
+    m = np.zeros(img.shape, np.uint8)
+    m[3, 4:15, 5:17] = 1                                  # single-slice ROI: that axis keeps its spacing (:509-511)
+    sp = (0.5, 0.5, 3.0)
+    ri, rm = IO.resampleImage(I.ArrayImage(img, sp), I.ArrayImage(m, sp), resampledPixelSpacing=[1.0, 1.0, 1.0])
+    oi, om, onew = RS.resample(img, m, sp, (1.0, 1.0, 1.0))
+    assert np.allclose(I.spacing_xyz(ri), onew) and onew[2] == 3.0
+    assert np.array_equal(I.as_array(ri), oi) and np.array_equal(I.as_array(rm), om)
+    with pytest.raises(ValueError):
+        IO.resampleImage(I.ArrayImage(img, sp), I.ArrayImage(np.zeros_like(m), sp), resampledPixelSpacing=[1, 1, 1])
+    with pytest.raises(ValueError):
+        IO.resampleImage(None, I.ArrayImage(m, sp), resampledPixelSpacing=[1, 1, 1])
