@@ -268,3 +268,68 @@ def test_plugin_resampleImage_single_slice_roi_and_errors(scipy_resampler):
         IO.resampleImage(I.ArrayImage(img, sp), I.ArrayImage(np.zeros_like(m), sp), resampledPixelSpacing=[1, 1, 1])
     with pytest.raises(ValueError):
         IO.resampleImage(None, I.ArrayImage(m, sp), resampledPixelSpacing=[1, 1, 1])
+
+
+# ---- getWaveletImage / _swt3: the level loop, the single wrap-padding of odd axes, cropping and the names the reference
+# generates, with the device transform of one level replaced by the oracle's (test only)
+@pytest.fixture()
+def numpy_swt(monkeypatch):
+    import torch
+    import filters_np as FN
+    from pyradiomics_b200 import imageoperations as IO
+    monkeypatch.setattr(IO, "_to_device", lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a))))
+
+    def level1(x, axes, lo, hi, z_range=None):
+        dec = FN.swtn_level1(x.numpy(), np.asarray(lo, float), np.asarray(hi, float), [int(a) for a in axes])
+        return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in dec.items()}
+
+    monkeypatch.setattr(IO, "swt_level1_device", level1)
+    return IO
+
+
+@pytest.mark.parametrize("shape,kw", [((9, 10, 11), {}), ((8, 9, 7), dict(level=2)), ((7, 8, 9), dict(level=2, start_level=1)),
+                                      ((6, 9, 8), dict(force2D=True, force2Ddimension=0)), ((11, 12), {}),
+                                      ((8, 8, 9), dict(wavelet="haar")), ((9, 7, 8), dict(wavelet="db2", level=2))])
+def test_plugin_wavelet_generator_equals_the_oracle_level_loop(numpy_swt, shape, kw):
+    import filters_np as FN
+    IO = numpy_swt
+    rng = np.random.default_rng(len(shape) + sum(shape))
+    img = rng.normal(100, 40, shape)
+    nd = len(shape)
+    axes = list(range(nd - 1, -1, -1))
+    if kw.get("force2D"):
+        axes.remove(kw.get("force2Ddimension", 0))
+    lo, hi = IO.wavelet_filters(kw.get("wavelet", "coif1"))
+    approx, levels = FN.swt3_levels(img, lo, hi, axes, kw.get("level", 1), kw.get("start_level", 0))
+    want = {}
+    for i, bands in enumerate(levels, start=1):
+        for key, arr in bands.items():
+            if set(key) == {"a"}:
+                continue
+            name = key.replace("a", "L").replace("d", "H")                   # imageoperations.py:954
+            want[(f"wavelet-{name}" if i == 1 else f"wavelet{i}-{name}")] = arr
+    want[f"wavelet-{'L' * len(axes)}" if len(levels) == 1 else f"wavelet{len(levels)}-{'L' * len(axes)}"] = approx
+    got = {name: I.as_array(im) for im, name, _ in IO.getWaveletImage(img, None, **kw)}
+    assert list(got) == list(want)                          # same names in the reference's order (imageoperations.py:877-896)
+    assert len(got) == kw.get("level", 1) * (2 ** len(axes) - 1) + 1
+    for name in want:
+        assert got[name].shape == img.shape
+        assert np.array_equal(got[name], want[name]), name
+
+
+def test_plugin_log_generator_checks_and_names(monkeypatch):
+    """getLoGImage's guards and names (reference imageoperations.py:807-836) with the device filter stubbed out"""
+    import torch
+    from pyradiomics_b200 import imageoperations as IO
+    calls = []
+    monkeypatch.setattr(IO, "_to_device", lambda a: torch.from_numpy(np.ascontiguousarray(np.asarray(a))))
+    monkeypatch.setattr(IO, "log_filter_device", lambda x, sigma, spacing_zyx: calls.append((sigma, spacing_zyx)) or x.to(torch.float32))
+    img = I.ArrayImage(np.zeros((8, 10, 12), np.int16), (0.5, 1.0, 2.0))
+    got = [(name, I.as_array(im).dtype) for im, name, _ in IO.getLoGImage(img, None, sigma=[1.0, 2.5, 3, 0.0, -1, 30.0])]
+    # sigma 30 mm / spacing 2 mm -> needs 16 planes, the image has 8: skipped; 0 and negative: skipped
+    assert [n for n, _ in got] == ["log-sigma-1-0-mm-3D", "log-sigma-2-5-mm-3D", "log-sigma-3-mm-3D"]
+    assert all(dt == np.float32 for _, dt in got)                      # ITK's filter returns Float32
+    assert calls == [(1.0, (2.0, 1.0, 0.5)), (2.5, (2.0, 1.0, 0.5)), (3.0, (2.0, 1.0, 0.5))]
+    assert list(IO.getLoGImage(I.ArrayImage(np.zeros((3, 10, 12)), (1, 1, 1)), None, sigma=[1.0])) == []      # an axis < 4
+    assert list(IO.getLoGImage(np.zeros((10, 12)), None, sigma=[1.0])) == []                                   # 2-D image
+    assert list(IO.getLoGImage(img, None)) == []                                                               # no sigma given
