@@ -333,3 +333,32 @@ def test_plugin_log_generator_checks_and_names(monkeypatch):
     assert list(IO.getLoGImage(I.ArrayImage(np.zeros((3, 10, 12)), (1, 1, 1)), None, sigma=[1.0])) == []      # an axis < 4
     assert list(IO.getLoGImage(np.zeros((10, 12)), None, sigma=[1.0])) == []                                   # 2-D image
     assert list(IO.getLoGImage(img, None)) == []                                                               # no sigma given
+
+
+def test_bin_edges_from_min_max_equal_the_reference_arithmetic_for_every_dtype():
+    """imageoperations._edges_from_minmax (the host half of binImage: the GPU only reduces min / max and digitizes) against
+    the reference's getBinEdges arithmetic on the ROI vector (oracle/pipeline.bin_edges = imageoperations.py:119-149), in the
+    image's own scalar type: float32 images round differently from float64 ones, integers promote in np.arange"""
+    from pyradiomics_b200 import imageoperations as IO
+    rng = np.random.default_rng(17)
+    n = 0
+    for dt in (np.int16, np.int32, np.float32, np.float64):
+        for trial in range(120):
+            scale = [1, 7, 300, 4000][trial % 4]
+            v = rng.normal(rng.uniform(-scale, scale), scale, 50)
+            if trial % 9 == 0:
+                v[:] = v[0]                                        # flat region
+            v = v.astype(dt)
+            for kw in (dict(binWidth=25), dict(binWidth=3.5), dict(binWidth=0.1), dict(binWidth=5000), dict(binWidth=7),
+                       dict(binCount=8), dict(binCount=64), dict(binCount=1)):
+                if np.issubdtype(dt, np.integer) and kw.get("binWidth") == 0.1 and scale == 4000:
+                    continue                                       # (tens of thousands of edges: nothing new)
+                with np.errstate(over="ignore"):                   # int16 + 2 * 5000 wraps in NumPy scalar arithmetic -- in both
+                    ref = PL.bin_edges(v, kw.get("binWidth", 25), kw.get("binCount"))
+                    got = IO._edges_from_minmax(v.min(), v.max(), dt, **kw)
+                assert np.asarray(got).shape == np.asarray(ref).shape, (dt, kw, v.min(), v.max())
+                assert np.array_equal(np.asarray(got, np.float64), np.asarray(ref, np.float64)), (dt, kw, v.min(), v.max())
+                # ... and digitizing with them gives the reference's levels
+                assert np.array_equal(np.digitize(v, np.asarray(got, np.float64)), np.digitize(v, ref))
+                n += 1
+    assert n > 3500
