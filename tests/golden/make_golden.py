@@ -129,6 +129,35 @@ def segment_goldens_resegmented():
     json.dump(expect, open(os.path.join(HERE, "segment_expect_extra.json"), "w"), indent=0, sort_keys=True)
 
 
+def segment_goldens_variants():
+    """settings the baseline CSVs do not exercise in segment mode, run through the reference's classes on three bundled
+    cases -> segment_expect_variants.json (same layout as segment_expect.json; oracle + plugin host-logic pins on the CPU box)"""
+    variants = {
+        "glcm": [dict(weightingNorm="manhattan"), dict(weightingNorm="euclidean"), dict(weightingNorm="infinity"),
+                 dict(distances=[1, 2, 3]), dict(symmetricalGLCM=False), dict(force2D=True, force2Ddimension=0), dict(binCount=16),
+                 dict(distances=[2], weightingNorm="euclidean", symmetricalGLCM=False)],
+        "glrlm": [dict(weightingNorm="manhattan"), dict(weightingNorm="euclidean"), dict(weightingNorm="infinity"),
+                  dict(force2D=True, force2Ddimension=0), dict(binCount=16)],
+        "glszm": [dict(force2D=True, force2Ddimension=0), dict(binCount=16), dict(binWidth=10)],
+        "gldm": [dict(gldm_a=2), dict(distances=[2]), dict(force2D=True, force2Ddimension=0), dict(gldm_a=1, distances=[1, 2])],
+        "ngtdm": [dict(distances=[1, 2]), dict(force2D=True, force2Ddimension=0), dict(binCount=16)],
+    }
+    expect = {}
+    for cname, cls in CLASSES.items():
+        for case in ("brain2", "breast1", "lung1"):
+            img, m, sp = rh.load_case(case)
+            for k, var in enumerate(variants[cname]):
+                kw = dict(binWidth=25)
+                kw.update(var)
+                if "binCount" in var:
+                    kw.pop("binWidth")
+                got = cls(sitk.Image(img, sp), sitk.Image(m.astype(np.uint8), sp), **kw).execute()
+                feats = {f: float(v) for f, v in got.items()}
+                expect.setdefault(cname, {})[f"{case}_x{k}"] = {"case": case, "settings": kw, "features": feats}
+                print("segment variant", cname, case, var, len(feats))
+    json.dump(expect, open(os.path.join(HERE, "segment_expect_variants.json"), "w"), indent=0, sort_keys=True)
+
+
 def voxel_volumes():
     vols = {}
     rng = np.random.default_rng(0)
@@ -421,6 +450,9 @@ def resample_goldens():
 
 
 if __name__ == "__main__":
+    if "--segment-variants-only" in sys.argv:
+        segment_goldens_variants()
+        sys.exit(0)
     if "--segment-extra-only" in sys.argv:
         segment_goldens_resegmented()
         sys.exit(0)

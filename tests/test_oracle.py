@@ -121,6 +121,20 @@ def test_pipeline_reproduces_reference_feature_baseline(seg, cname):
 
 
 @pytest.mark.parametrize("cname", PL.CLASS_NAMES)
+def test_pipeline_reproduces_reference_runs_of_settings_the_baselines_do_not_cover(seg, cname):
+    """weighting norms, several distances, asymmetric GLCM, force2D, binCount, gldm_a in SEGMENT mode: runs of the reference's
+    classes on three bundled cases (tests/golden/segment_expect_variants.json, make_golden.py --segment-variants-only)"""
+    cases, _ = seg
+    expect = json.load(open(os.path.join(GOLDEN, "segment_expect_variants.json")))[cname]
+    assert len(expect) >= 9
+    for test, e in expect.items():
+        c = e["case"]
+        got = PL.extract(cname, cases[c + "_image"], cases[c + "_mask"], spacing_zyx=cases[c + "_spacing"][::-1], **e["settings"])
+        for f, v in e["features"].items():
+            assert np.isclose(got[f], v, rtol=1e-9, atol=1e-12, equal_nan=True), (cname, test, e["settings"], f, got[f], v)
+
+
+@pytest.mark.parametrize("cname", PL.CLASS_NAMES)
 def test_pipeline_reproduces_the_resegmented_baseline_columns(seg, cname):
     """`<case>_flatRegion` (one gray level: the single-edge branch of getBinEdges, every class on a flat ROI),
     `<case>_resegmentation` (masks resegmented by the reference's own resegmentMask) and `<case>_normalization` (float image,

@@ -79,6 +79,21 @@ def test_plugin_classes_over_oracle_matrices_match_every_baseline_column(oracle_
             assert abs(float(got[f]) - v) <= 1e-9 * max(abs(v), 1e-12), (cname, test, f, float(got[f]), v)
 
 
+@pytest.mark.parametrize("cname", CLASSES)
+def test_plugin_classes_over_oracle_matrices_match_reference_runs_of_other_settings(oracle_device, cname):
+    """weighting norms (featureclasses._weights), several distances, asymmetric GLCM, force2D, binCount, gldm_a"""
+    cases = np.load(os.path.join(GOLDEN, "segment_cases.npz"))
+    expect = json.load(open(os.path.join(GOLDEN, "segment_expect_variants.json")))[cname]
+    for test, e in expect.items():
+        c = e["case"]
+        sp = cases[c + "_spacing"]
+        got = FC.FEATURE_CLASSES[cname](I.ArrayImage(cases[c + "_image"], sp), I.ArrayImage(cases[c + "_mask"].astype(np.uint8), sp),
+                                        **e["settings"]).execute()
+        assert set(got) == set(e["features"]), (test, set(got) ^ set(e["features"]))
+        for f, v in e["features"].items():
+            assert np.isclose(float(got[f]), v, rtol=1e-9, atol=1e-12, equal_nan=True), (cname, test, e["settings"], f, float(got[f]), v)
+
+
 @pytest.mark.parametrize("case", ["brain1", "brain2", "breast1", "lung1", "lung2"])
 def test_plugin_processed_matrices_over_oracle_matrices_match_the_golden_matrices(oracle_device, case):
     """reference tests/test_matrices.py:35-65 through the product's _calculateMatrix post-processing"""
