@@ -377,3 +377,42 @@ def test_bin_edges_from_min_max_equal_the_reference_arithmetic_for_every_dtype()
                 assert np.array_equal(np.digitize(v, np.asarray(got, np.float64)), np.digitize(v, ref))
                 n += 1
     assert n > 3500
+
+
+# ---- cmatrices: argument errors are raised on the host, before anything touches the device, with the reference's exception
+# types (SURVEY.md 8b "Error conventions") -- checked against the compiled reference extension itself
+def _ref_cmatrices():
+    import importlib.util
+    import glob as _glob
+    so = _glob.glob(os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "_cmatrices*.so"))
+    if not so:
+        pytest.skip("oracle/_ref is not built (needs /root/reference)")
+    spec = importlib.util.spec_from_file_location("_cmatrices", so[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+BAD_CALLS = {
+    "ndim mismatch": lambda cm, i, m: cm.calculate_glcm(i, m[0], np.array([1]), 8, False, -1),
+    "shape mismatch": lambda cm, i, m: cm.calculate_glcm(i, m[:, :4], np.array([1]), 8, False, -1),
+    "voxels without kernelRadius": lambda cm, i, m: cm.calculate_glcm(i, m, np.array([1]), 8, False, -1, 0, np.zeros((3, 2), np.int32)),
+    "voxels with the wrong first dimension": lambda cm, i, m: cm.calculate_glrlm(i, m, 8, 6, False, -1, 1, np.zeros((2, 4), np.int32)),
+    "voxels 1-D": lambda cm, i, m: cm.calculate_ngtdm(i, m, np.array([1]), 8, False, -1, 1, np.zeros(3, np.int32)),
+    "distances 2-D": lambda cm, i, m: cm.calculate_gldm(i, m, np.ones((2, 2), np.int32), 8, 0, False, -1),
+    "size 2-D": lambda cm, i, m: cm.generate_angles(np.ones((2, 3), np.int32), np.array([1]), 0, False, -1),
+    "no angle": lambda cm, i, m: cm.generate_angles(np.array([5, 5, 5], np.int32), np.array([9]), 0, False, -1),
+}
+
+
+@pytest.mark.parametrize("what", list(BAD_CALLS))
+def test_cmatrices_argument_errors_have_the_reference_exception_types(what):
+    ref = _ref_cmatrices()
+    img = np.ones((4, 5, 6), np.int32)
+    msk = np.ones((4, 5, 6), bool)
+    with pytest.raises(Exception) as want:
+        BAD_CALLS[what](ref, img, msk)
+    with pytest.raises(Exception) as got:
+        BAD_CALLS[what](cmatrices, img, msk)
+    assert type(got.value) is type(want.value), (what, repr(got.value), repr(want.value))
+    assert type(got.value) in (ValueError, RuntimeError)
