@@ -214,6 +214,10 @@ def voxel_volumes_extra():
     # (l) binWidth on negative intensities (lower bound below zero)
     vols["negative"] = dict(image=(rng.integers(-260, 190, (6, 6, 6))).astype(np.int32), mask=rng.random((6, 6, 6)) > 0.1,
                             kw=dict(binWidth=50))
+    # (m) unmasked kernel: the windows see every voxel of the image, only ROI voxels get a value (base.py:100-104)
+    vols["unmasked_kernel"] = dict(image=rng.integers(1, 9, (6, 7, 8)).astype(np.int32),
+                                   mask=blob[:6, :7, :7].repeat(2, 2)[:, :, :8] & (rng.random((6, 7, 8)) > 0.2),
+                                   kw=dict(binWidth=1, maskedKernel=False))
     return vols
 
 

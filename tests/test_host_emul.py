@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 import cmatrices_oracle as O
+import pipeline as PL
 from helpers import assert_maps_close, binned, ref_map, voxel_goldens
 from pyradiomics_b200 import _lib
 
@@ -71,20 +72,29 @@ def test_feature_name_tables_match_library_order():
 
 @pytest.mark.parametrize("name,z,kw", voxel_goldens(extra=True), ids=[g[0] for g in voxel_goldens(extra=True)])
 def test_device_math_on_host_matches_reference_maps(emul, name, z, kw):
-    lev, levels, Ng = binned(z, kw)
+    centers = None
+    if kw.get("maskedKernel", True):
+        lev, levels, Ng = binned(z, kw)
+    else:
+        # unmasked kernel (base.py:100-104): every voxel of the image is binned and seen by the windows, the ROI only
+        # selects the centre voxels (the kernel's `centers` argument, what the plugin passes for maskedKernel=False)
+        lev, _, levels, Ng = PL.bin_image(z["image"], np.ones(z["mask"].shape, bool), kw.get("binWidth", 25), kw.get("binCount"))
+        centers = np.ascontiguousarray(z["mask"], dtype=np.uint8)
     lev16 = np.ascontiguousarray(lev, dtype=np.uint16)
-    s = _lib.make_settings(Ng, len(levels), spacing_zyx=z["spacing"][::-1], **kw)
+    kws = {k: v for k, v in kw.items() if k != "maskedKernel"}
+    s = _lib.make_settings(Ng, len(levels), spacing_zyx=z["spacing"][::-1], **kws)
     Zs, Ys, Xs = lev.shape
     ang = O.generate_angles(lev.shape, kw.get("distances", [1]), 0, s.force2D, s.force2Ddimension)
     r3 = [0 if (s.force2D and s.force2Ddimension == k) else s.kernelRadius for k in range(3)]
     alive = alive_mask_bruteforce(lev, z["mask"], ang, r3)
     for cid, cname in enumerate(_lib.CLASSES):
         out = np.zeros((len(NAMES[cname]), Zs, Ys, Xs))
-        rc = emul.emul_voxel_features(cid, lev16.ctypes.data_as(C.c_void_p), None, Zs, Ys, Xs, C.byref(s),
-                                      alive.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        rc = emul.emul_voxel_features(cid, lev16.ctypes.data_as(C.c_void_p), None if centers is None else centers.ctypes.data_as(C.c_void_p),
+                                      Zs, Ys, Xs, C.byref(s), alive.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
         assert rc == 0
         for k, f in enumerate(NAMES[cname]):
-            assert_maps_close(out[k], ref_map(z, cname, f), f"{name}/{cname}/{f}", rtol=1e-7, atol=1e-9)
+            got = out[k] if centers is None else np.where(z["mask"], out[k], ref_map(z, cname, f))      # (outside the ROI: initValue)
+            assert_maps_close(got, ref_map(z, cname, f), f"{name}/{cname}/{f}", rtol=1e-7, atol=1e-9)
 
 
 @pytest.mark.parametrize("name,r", [("r1", 1), ("r2", 2)])
