@@ -218,6 +218,9 @@ def voxel_volumes_extra():
     vols["unmasked_kernel"] = dict(image=rng.integers(1, 9, (6, 7, 8)).astype(np.int32),
                                    mask=blob[:6, :7, :7].repeat(2, 2)[:, :, :8] & (rng.random((6, 7, 8)) > 0.2),
                                    kw=dict(binWidth=1, maskedKernel=False))
+    # (n) a 2-D image (Nd = 2: 4 / 8 angles, 3 x 3 windows)
+    vols["image2d"] = dict(image=rng.integers(1, 7, (9, 10)).astype(np.int32), mask=rng.random((9, 10)) > 0.12, spacing=(0.8, 1.1),
+                           kw=dict(binWidth=1))
     return vols
 
 

@@ -80,21 +80,26 @@ def test_device_math_on_host_matches_reference_maps(emul, name, z, kw):
         # selects the centre voxels (the kernel's `centers` argument, what the plugin passes for maskedKernel=False)
         lev, _, levels, Ng = PL.bin_image(z["image"], np.ones(z["mask"].shape, bool), kw.get("binWidth", 25), kw.get("binCount"))
         centers = np.ascontiguousarray(z["mask"], dtype=np.uint8)
+    mask, sp_zyx = z["mask"], tuple(z["spacing"][::-1])
+    if lev.ndim == 2:                        # a 2-D image runs as one plane, like featureclasses.levels3d / _voxel_settings
+        lev, mask, sp_zyx = lev[None], mask[None], (1.0,) + sp_zyx
+        centers = None if centers is None else centers[None]
     lev16 = np.ascontiguousarray(lev, dtype=np.uint16)
     kws = {k: v for k, v in kw.items() if k != "maskedKernel"}
-    s = _lib.make_settings(Ng, len(levels), spacing_zyx=z["spacing"][::-1], **kws)
+    s = _lib.make_settings(Ng, len(levels), spacing_zyx=sp_zyx, **kws)
     Zs, Ys, Xs = lev.shape
     ang = O.generate_angles(lev.shape, kw.get("distances", [1]), 0, s.force2D, s.force2Ddimension)
     r3 = [0 if (s.force2D and s.force2Ddimension == k) else s.kernelRadius for k in range(3)]
-    alive = alive_mask_bruteforce(lev, z["mask"], ang, r3)
+    alive = alive_mask_bruteforce(lev, mask, ang, r3)
     for cid, cname in enumerate(_lib.CLASSES):
         out = np.zeros((len(NAMES[cname]), Zs, Ys, Xs))
         rc = emul.emul_voxel_features(cid, lev16.ctypes.data_as(C.c_void_p), None if centers is None else centers.ctypes.data_as(C.c_void_p),
                                       Zs, Ys, Xs, C.byref(s), alive.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
         assert rc == 0
         for k, f in enumerate(NAMES[cname]):
-            got = out[k] if centers is None else np.where(z["mask"], out[k], ref_map(z, cname, f))      # (outside the ROI: initValue)
-            assert_maps_close(got, ref_map(z, cname, f), f"{name}/{cname}/{f}", rtol=1e-7, atol=1e-9)
+            ref = ref_map(z, cname, f).reshape(out[k].shape)
+            got = out[k] if centers is None else np.where(mask, out[k], ref)      # (outside the ROI: initValue)
+            assert_maps_close(got, ref, f"{name}/{cname}/{f}", rtol=1e-7, atol=1e-9)
 
 
 @pytest.mark.parametrize("name,r", [("r1", 1), ("r2", 2)])

@@ -416,3 +416,21 @@ def test_cmatrices_argument_errors_have_the_reference_exception_types(what):
         BAD_CALLS[what](cmatrices, img, msk)
     assert type(got.value) is type(want.value), (what, repr(got.value), repr(want.value))
     assert type(got.value) in (ValueError, RuntimeError)
+
+
+def test_plugin_voxel_settings_of_a_2d_image_describe_one_plane(oracle_device):
+    """a 2-D image runs through the 3-D kernels as a single plane: spacing gets a leading 1, a force2D dimension moves up by
+    one axis (featureclasses._voxel_settings) -- the settings the emulated kernel reproduces the reference's 2-D maps with
+    (tests/test_host_emul.py, golden voxelx_image2d)"""
+    z = np.load(os.path.join(GOLDEN, "voxelx_image2d.npz"))
+    sp = tuple(float(v) for v in z["spacing"])
+    obj = FC.RadiomicsGLCM(I.ArrayImage(z["image"], sp), I.ArrayImage(z["mask"].astype(np.uint8), sp), voxelBased=True, binWidth=1)
+    s = obj._voxel_settings()
+    assert (s.kernelRadius, s.force2D, s.ndist, s.distances[0], s.symmetricalGLCM) == (1, 0, 1, 1, 1)
+    assert tuple(s.spacing_zyx) == (1.0, sp[1], sp[0])
+    assert s.Ng == int(obj.coefficients["Ng"]) and s.n_roi_levels == len(obj.coefficients["grayLevels"])
+    obj2 = FC.RadiomicsGLRLM(I.ArrayImage(z["image"], sp), I.ArrayImage(z["mask"].astype(np.uint8), sp), voxelBased=True, binWidth=1,
+                             force2D=True, force2Ddimension=1, weightingNorm="euclidean", kernelRadius=2, initValue=-1.0)
+    s2 = obj2._voxel_settings()
+    assert (s2.force2D, s2.force2Ddimension, s2.kernelRadius, s2.initValue) == (1, 2, 2, -1.0)
+    assert obj.masked is True and obj2.voxelBased is True
