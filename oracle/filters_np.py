@@ -17,7 +17,6 @@ reconstruction / Parseval for the wavelet, agreement with an analytic Gaussian-L
 """
 from __future__ import annotations
 
-import itertools
 
 import numpy as np
 

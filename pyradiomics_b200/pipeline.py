@@ -10,7 +10,6 @@
 """
 from __future__ import annotations
 
-import numpy as np
 import torch
 
 from . import _lib, featureclasses as FC, imageoperations as IO, voxel
